@@ -1,0 +1,1092 @@
+// libm2m_b200: context, weight arena, workspaces and the host-side orchestration of the hot path
+// (log-mel -> conditioning -> T5 encoder -> cross-KV -> KV-cached greedy decode).  C ABI in
+// include/m2m_b200.h.  One context per GPU; kernels are launched on the caller's stream.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+namespace m2m {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes, int64_t* generation) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3);  // 12.5 % slack to avoid regrowth on nearby sizes
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      return M2M_ERR_OOM;
+    }
+    cap = want;
+    if (generation) ++*generation;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct EncLayerW {
+  float *ln0, *ln1;
+  void *wqkv, *wo, *wi, *wffo;  // T-typed
+};
+struct DecLayerW {
+  float *ln0, *ln1, *ln2;
+  void *wqkv, *wo, *wcq, *wckv, *wco, *wi, *wffo;
+};
+
+struct GraphKey {
+  int B = -1, L = -1, max_length = -1;
+  int64_t generation = -1;
+  uint32_t flags = 0;
+};
+
+}  // namespace m2m
+
+using namespace m2m;
+
+struct m2m_ctx {
+  m2m_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  bool finalized = false;
+  bool model_ready = false;  // false: frontend-only context (window + filterbank, no transformer)
+  uint32_t flags = 1u | 4u;
+  std::map<std::string, std::vector<float>> staged;
+  std::vector<int32_t> enc_lut, dec_lut;
+
+  // weight arena (one allocation) + typed views
+  DevBuf arena;
+  std::vector<EncLayerW> enc;
+  std::vector<DecLayerW> dec;
+  float *enc_final_ln = nullptr, *dec_final_ln = nullptr, *shared = nullptr, *enc_bias = nullptr, *dec_bias = nullptr,
+        *dec_bias_seq = nullptr;
+  void* lm_head = nullptr;
+  float *window = nullptr, *dft_basis = nullptr, *band_w = nullptr, *cond_emb = nullptr;
+  int *band_start = nullptr, *band_len = nullptr, *cond_off = nullptr, *cond_rows = nullptr;
+  int n_freq = 0, dft_rows = 0, max_band = 32, enc_bias_ld = 0;
+  void* dft_basis_tc = nullptr;  // bf16 split basis for the tcgen05 path (optional)
+
+  // workspaces
+  int64_t generation = 0;
+  DevBuf mel_power, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
+  DevBuf ckv, skv;  // cross / self KV caches, all layers
+  DevBuf dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err;
+  DevBuf tf_x, tf_h, tf_qkv, tf_ao, tf_g, tf_q;  // teacher-forced decoder
+  DevBuf host_wave, host_cond, host_tokens;      // m2m_transcribe_host device staging
+  int* h_done = nullptr;                         // pinned
+  cudaEvent_t poll_ev = nullptr;
+  cudaStream_t own_stream = nullptr;
+
+  cudaGraphExec_t step_graph = nullptr;
+  GraphKey graph_key;
+  size_t graph_nodes = 0;
+
+  std::vector<cudaEvent_t> ev_pool;
+  m2m_stats stats;
+};
+
+namespace m2m {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define LAUNCH_CHECK(ctx)                                                                    \
+  do {                                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return M2M_ERR_CUDA;                                                                   \
+    }                                                                                        \
+    (ctx)->stats.kernel_launches++;                                                          \
+  } while (0)
+
+// ------------------------------------------------------------------ GEMM dispatch
+// C = A[M,K] . W[N,K]^T with epilogue.  bf16 operands with large M go to the tcgen05 kernel,
+// everything else (fp32 parity mode, small M) to the CUDA-core kernel.
+template <typename T, typename Epi>
+static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K, Epi epi, const DecState* st,
+                cudaStream_t s) {
+  if (M == 0) return 0;
+  cudaError_t e = launch_gemm_simt(RowMajorA<T>{A, lda}, W, K, M, N, K, epi, st, s, c->num_sms);
+  if (e != cudaSuccess) {
+    set_error("gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
+    return M2M_ERR_CUDA;
+  }
+  c->stats.kernel_launches++;
+  return 0;
+}
+
+template <typename TO>
+static int rmsnorm(m2m_ctx* c, const float* x, const float* w, TO* y, size_t rows, const DecState* st, cudaStream_t s) {
+  if (rows == 0) return 0;
+  int D = c->cfg.d_model;
+  unsigned blocks = (unsigned)((rows + 7) / 8);
+  rmsnorm_kernel<TO><<<blocks, 256, 0, s>>>(x, w, y, (int)rows, D, c->cfg.ln_eps, st);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+template <typename T, bool CAUSAL>
+static int seq_attn(m2m_ctx* c, const T* Q, int ldq, const T* K, const T* V, int ldkv, T* O, int ldo, int B, int Lq,
+                    int Lk, const float* bias, int bias_ld, int bias_zero, cudaStream_t s) {
+  size_t smem = ((size_t)Lk * (65 + 64) + 8 * (size_t)Lk) * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_error("sequence attention: key length %d needs %zu B of shared memory (max 227 KB)", Lk, smem);
+    return M2M_ERR_INVALID;
+  }
+  auto kern = seq_attn_kernel<T, CAUSAL>;
+  M2M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int q_tile = Lq <= 96 ? Lq : 64;
+  if (q_tile < 8) q_tile = 8;
+  dim3 grid((Lq + q_tile - 1) / q_tile, c->cfg.n_heads, B);
+  kern<<<grid, 256, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Lq, Lk, bias, bias_ld, bias_zero, q_tile);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+// ------------------------------------------------------------------ log-mel
+static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_mel, cudaStream_t s) {
+  const m2m_config& g = c->cfg;
+  M2M_REQUIRE(B >= 0 && S > g.n_fft / 2, "logmel: need S > n_fft/2 = %d for reflect padding (got S=%d)", g.n_fft / 2, S);
+  if (B == 0) return 0;
+  const int T = 1 + S / g.hop;
+  const size_t M = (size_t)B * T;
+  const int ldp = (int)align_up(c->n_freq, 4);
+  // frames are processed in slabs so that the power spectrum stays L2-resident between the two kernels
+  const size_t slab_rows = 16384;  // 16384 x 1028 x 4 B = 67 MB < 126 MB L2
+  M2M_TRY(c->mel_power.ensure(std::min(M, slab_rows) * ldp * sizeof(float), &c->generation));
+  for (size_t r0 = 0; r0 < M; r0 += slab_rows) {
+    size_t rows = std::min(slab_rows, M - r0);
+    FrameA a{d_wave, c->window, S, T, g.hop, g.n_fft / 2, (int)r0};
+    cudaError_t e = launch_gemm_simt(a, c->dft_basis, g.n_fft, (int)rows, c->dft_rows, g.n_fft,
+                                     EpiPower{c->mel_power.as<float>(), ldp, c->n_freq}, nullptr, s, c->num_sms);
+    if (e != cudaSuccess) {
+      set_error("logmel DFT launch failed: %s", cudaGetErrorString(e));
+      return M2M_ERR_CUDA;
+    }
+    c->stats.kernel_launches++;
+    dim3 grid((g.d_model + 127) / 128, (unsigned)std::min<size_t>(rows, 4096));
+    mel_band_log_kernel<<<grid, 128, 0, s>>>(c->mel_power.as<float>(), ldp, c->band_start, c->band_len, c->band_w,
+                                             c->max_band, d_mel + r0 * g.d_model, rows, g.d_model);
+    LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+
+static int condition_impl(m2m_ctx* c, const float* d_feature, const int64_t* d_cond, int B, int T, float* d_embeds,
+                          cudaStream_t s) {
+  if (B == 0) return 0;
+  const m2m_config& g = c->cfg;
+  M2M_TRY(c->dec_err.ensure(sizeof(int), nullptr));
+  M2M_CUDA(cudaMemsetAsync(c->dec_err.p, 0, sizeof(int), s));
+  size_t total = (size_t)B * (T + g.n_cond) * (g.d_model / 4);
+  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  condition_kernel<<<blocks, 256, 0, s>>>(d_feature, d_cond, c->cond_emb, c->cond_off, c->cond_rows, d_embeds, B, T,
+                                          g.d_model, g.n_cond, c->dec_err.as<int>());
+  LAUNCH_CHECK(c);
+  int err = 0;
+  M2M_CUDA(cudaMemcpyAsync(&err, c->dec_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  M2M_CUDA(cudaStreamSynchronize(s));
+  M2M_REQUIRE(err == 0, "conditioning: cond_index out of range (IndexError in the reference's nn.Embedding)");
+  return 0;
+}
+
+// ------------------------------------------------------------------ encoder
+template <typename T>
+static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d_out, bool keep_typed, cudaStream_t s) {
+  const m2m_config& g = c->cfg;
+  M2M_REQUIRE(L >= 1 && L <= g.max_enc_len, "encoder length %d outside [1, %d]", L, g.max_enc_len);
+  if (B == 0) return 0;
+  const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff;
+  const size_t M = (size_t)B * L;
+  M2M_REQUIRE(M < (1u << 31) / 4, "encoder batch too large: %zu rows", M);
+  M2M_TRY(c->enc_x.ensure(M * D * sizeof(float), &c->generation));
+  M2M_TRY(c->enc_h.ensure(M * D * sizeof(T), &c->generation));
+  M2M_TRY(c->enc_qkv.ensure(M * 3 * I * sizeof(T), &c->generation));
+  M2M_TRY(c->enc_ao.ensure(M * I * sizeof(T), &c->generation));
+  M2M_TRY(c->enc_g.ensure(M * F * sizeof(T), &c->generation));
+  float* x = c->enc_x.as<float>();
+  T* h = c->enc_h.as<T>();
+  T* qkv = c->enc_qkv.as<T>();
+  T* ao = c->enc_ao.as<T>();
+  T* gg = c->enc_g.as<T>();
+  M2M_CUDA(cudaMemcpyAsync(x, d_embeds, M * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  for (int l = 0; l < g.n_layers; ++l) {
+    const EncLayerW& w = c->enc[l];
+    M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, M, nullptr, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
+    M2M_TRY((seq_attn<T, false>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, 3 * I, ao, I, B, L, L, c->enc_bias, c->enc_bias_ld,
+                                g.max_enc_len - 1, s)));
+    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
+    M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, M, nullptr, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));
+    M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, (int)M, D, F, EpiResidual{x, D}, nullptr, s));
+  }
+  if (d_out) M2M_TRY(rmsnorm<float>(c, x, c->enc_final_ln, d_out, M, nullptr, s));
+  if (keep_typed) {
+    M2M_TRY(c->enc_out.ensure(M * D * sizeof(T), &c->generation));
+    M2M_TRY(rmsnorm<T>(c, x, c->enc_final_ln, c->enc_out.as<T>(), M, nullptr, s));
+  }
+  return 0;
+}
+
+// cross-attention K/V of every decoder layer from the typed encoder output: ckv[l] = [B*L, 2I]
+template <typename T>
+static int cross_kv_impl(m2m_ctx* c, const T* enc_out, int B, int L, cudaStream_t s) {
+  const m2m_config& g = c->cfg;
+  const int D = g.d_model, I = g.n_heads * g.d_kv;
+  const size_t M = (size_t)B * L;
+  M2M_TRY(c->ckv.ensure((size_t)g.n_layers * M * 2 * I * sizeof(T), &c->generation));
+  for (int l = 0; l < g.n_layers; ++l) {
+    T* dst = c->ckv.as<T>() + (size_t)l * M * 2 * I;
+    M2M_TRY(gemm<T>(c, enc_out, D, (const T*)c->dec[l].wckv, (int)M, 2 * I, D, EpiStore<T>{dst, 2 * I}, nullptr, s));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ one decode step (a8, a9)
+struct StepTiming {
+  bool on = false;
+  size_t next = 0;
+};
+
+template <typename T>
+static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const int64_t* forced, float* logits_all,
+                              bool skip_finished, StepTiming* tm, cudaStream_t s) {
+  const m2m_config& g = c->cfg;
+  const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
+  const int Tmax = max_length;  // cache positions per row
+  DecState* st = c->dec_state.as<DecState>();
+  float* x = c->dec_x.as<float>();
+  T* h = c->dec_h.as<T>();
+  T* q = c->dec_q.as<T>();
+  T* ao = c->dec_ao.as<T>();
+  T* gg = c->dec_g.as<T>();
+  float* logits = c->dec_logits.as<float>();
+  uint8_t* fin = c->dec_finished.as<uint8_t>();
+  const uint8_t* fin_skip = skip_finished ? fin : nullptr;
+  const size_t self_layer = (size_t)B * Tmax * I;  // elements per K (or V) per layer
+  const size_t cross_layer = (size_t)B * L * 2 * I;
+  constexpr bool FAST = !std::is_same<T, float>::value;
+  dim3 agrid(g.n_heads / 4, B);
+  for (int l = 0; l < g.n_layers; ++l) {
+    const DecLayerW& w = c->dec[l];
+    T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer;
+    T* vc = kc + self_layer;
+    const T* ck = c->ckv.as<T>() + (size_t)l * cross_layer;
+    M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, B, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, B, 3 * I, D, EpiQKVCache<T>{q, kc, vc, I, (size_t)Tmax * I}, st, s));
+    if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
+    decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, I, 0, c->dec_bias,
+                                                            g.max_positions, ao, g.n_heads, st, fin_skip);
+    LAUNCH_CHECK(c);
+    if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
+    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, B, D, I, EpiResidual{x, D}, st, s));
+    M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, B, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, B, I, D, EpiStore<T>{q, I}, st, s));
+    decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, ck + I, (size_t)L * 2 * I, 2 * I, L, nullptr, 0, ao,
+                                                             g.n_heads, st, fin_skip);
+    LAUNCH_CHECK(c);
+    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, B, D, I, EpiResidual{x, D}, st, s));
+    M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, B, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, B, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
+    M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, B, D, F, EpiResidual{x, D}, st, s));
+  }
+  M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, B, st, s));
+  M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, B, V, D, EpiStore<float>{logits, V}, st, s));
+  select_token_kernel<<<B, 128, 0, s>>>(logits, V, c->dec_tokens.as<int64_t>(), max_length, forced, fin, c->shared, x, D,
+                                        logits_all, st, g.pad_id, g.eos_id);
+  LAUNCH_CHECK(c);
+  step_advance_kernel<<<1, 1, 0, s>>>(st, forced == nullptr ? 1 : 0);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+__global__ void decode_init_kernel(int64_t* tokens, int ld, uint8_t* finished, float* x, const float* table, int D,
+                                   int B, int bos, DecState* st, int max_length) {
+  int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    tokens[(size_t)b * ld] = bos;
+    finished[b] = 0;
+    if (b == 0) {
+      st->t = 0;
+      st->done = max_length <= 1 ? 1 : 0;
+      st->final_len = max_length <= 1 ? 1 : max_length;
+      st->unfinished = 0;
+      st->max_length = max_length;
+    }
+  }
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(x + (size_t)b * D)[i] = reinterpret_cast<const float4*>(table + (size_t)bos * D)[i];
+}
+
+template <typename T>
+static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, int L, int max_length,
+                                     const int64_t* d_forced, int64_t* d_tokens, float* d_logits, int* out_len,
+                                     cudaStream_t s) {
+  const m2m_config& g = c->cfg;
+  M2M_REQUIRE(max_length >= 1 && max_length <= g.max_positions, "max_length %d outside [1, %d]", max_length,
+              g.max_positions);
+  M2M_REQUIRE(B >= 0, "negative batch");
+  if (out_len) *out_len = 1;
+  if (B == 0) return 0;
+  const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+  M2M_TRY(encode_impl<T>(c, d_embeds, B, L, nullptr, true, s));
+  M2M_TRY(cross_kv_impl<T>(c, c->enc_out.as<T>(), B, L, s));
+
+  M2M_TRY(c->skv.ensure((size_t)g.n_layers * 2 * B * max_length * I * sizeof(T), &c->generation));
+  M2M_TRY(c->dec_x.ensure((size_t)B * D * sizeof(float), &c->generation));
+  M2M_TRY(c->dec_h.ensure((size_t)B * D * sizeof(T), &c->generation));
+  M2M_TRY(c->dec_q.ensure((size_t)B * I * sizeof(T), &c->generation));
+  M2M_TRY(c->dec_ao.ensure((size_t)B * I * sizeof(T), &c->generation));
+  M2M_TRY(c->dec_g.ensure((size_t)B * F * sizeof(T), &c->generation));
+  M2M_TRY(c->dec_logits.ensure((size_t)B * V * sizeof(float), &c->generation));
+  M2M_TRY(c->dec_finished.ensure((size_t)B, &c->generation));
+  M2M_TRY(c->dec_tokens.ensure((size_t)B * max_length * sizeof(int64_t), &c->generation));
+  M2M_TRY(c->dec_state.ensure(sizeof(DecState), &c->generation));
+
+  int64_t* tokens = c->dec_tokens.as<int64_t>();
+  M2M_CUDA(cudaMemsetAsync(tokens, 0, (size_t)B * max_length * sizeof(int64_t), s));  // pad_id == 0 rows
+  if (g.pad_id != 0) {
+    set_error("pad_token_id != 0 is not supported");
+    return M2M_ERR_INVALID;
+  }
+  decode_init_kernel<<<B, 128, 0, s>>>(tokens, max_length, c->dec_finished.as<uint8_t>(), c->dec_x.as<float>(),
+                                       c->shared, D, B, g.bos_id, c->dec_state.as<DecState>(), max_length);
+  LAUNCH_CHECK(c);
+
+  const int n_steps = max_length - 1;
+  const bool timing = (c->flags & 2u) != 0;
+  const bool plain = d_forced == nullptr && d_logits == nullptr;
+  const bool use_graph = (c->flags & 1u) && plain && !timing;
+  const bool skip_finished = (c->flags & 4u) && plain;
+  StepTiming tm;
+  if (timing) {
+    size_t need = (size_t)n_steps * g.n_layers * 2;
+    while (c->ev_pool.size() < need) {
+      cudaEvent_t e;
+      M2M_CUDA(cudaEventCreate(&e));
+      c->ev_pool.push_back(e);
+    }
+    tm.on = true;
+  }
+
+  if (use_graph && n_steps > 0) {
+    GraphKey key;
+    key.B = B; key.L = L; key.max_length = max_length; key.generation = c->generation; key.flags = c->flags;
+    bool hit = c->step_graph && c->graph_key.B == B && c->graph_key.L == L && c->graph_key.max_length == max_length &&
+               c->graph_key.generation == c->generation && c->graph_key.flags == c->flags;
+    if (!hit) {
+      if (c->step_graph) {
+        cudaGraphExecDestroy(c->step_graph);
+        c->step_graph = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      int64_t launches_before = c->stats.kernel_launches;
+      // capture on the context's own stream (the caller's may be the legacy default stream, which
+      // cannot be captured); the instantiated graph is then launched on the caller's stream.
+      cudaStream_t cs = c->own_stream;
+      M2M_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      int rc = decode_step_launch<T>(c, B, L, max_length, nullptr, nullptr, skip_finished, nullptr, cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      c->graph_nodes = (size_t)(c->stats.kernel_launches - launches_before);
+      c->stats.kernel_launches = launches_before;
+      if (rc != 0) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess) {
+        set_error("decode-step graph capture failed: %s", cudaGetErrorString(ce));
+        return M2M_ERR_CUDA;
+      }
+      M2M_CUDA(cudaGraphInstantiate(&c->step_graph, graph, 0));
+      cudaGraphDestroy(graph);
+      c->graph_key = key;
+    }
+  }
+
+  M2M_CUDA(cudaEventCreate(&ev_begin));
+  M2M_CUDA(cudaEventCreate(&ev_end));
+  M2M_CUDA(cudaEventRecord(ev_begin, s));
+  *c->h_done = 0;
+  bool poll_pending = false;
+  int steps_launched = 0;
+  for (int step = 0; step < n_steps; ++step) {
+    if (use_graph) {
+      M2M_CUDA(cudaGraphLaunch(c->step_graph, s));
+      c->stats.kernel_launches += (int64_t)c->graph_nodes;
+    } else {
+      M2M_TRY(decode_step_launch<T>(c, B, L, max_length, d_forced, d_logits, skip_finished, &tm, s));
+    }
+    ++steps_launched;
+    // lagging, non-blocking stop detection: the device sets st->done; later launches are no-ops
+    if (d_forced == nullptr && (step & 15) == 15) {
+      if (poll_pending && cudaEventQuery(c->poll_ev) == cudaSuccess) {
+        poll_pending = false;
+        if (*c->h_done) break;
+      }
+      if (!poll_pending) {
+        M2M_CUDA(cudaMemcpyAsync(c->h_done, &c->dec_state.as<DecState>()->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        M2M_CUDA(cudaEventRecord(c->poll_ev, s));
+        poll_pending = true;
+      }
+    }
+  }
+  M2M_CUDA(cudaEventRecord(ev_end, s));
+  DecState hst;
+  M2M_CUDA(cudaMemcpyAsync(&hst, c->dec_state.p, sizeof(DecState), cudaMemcpyDeviceToHost, s));
+  if (d_tokens)
+    M2M_CUDA(cudaMemcpyAsync(d_tokens, tokens, (size_t)B * max_length * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  M2M_CUDA(cudaStreamSynchronize(s));
+  if (n_steps > 0 && !hst.done) {
+    set_error("internal: decode loop ended without reaching a stop condition (t=%d)", hst.t);
+    return M2M_ERR_STATE;
+  }
+  if (out_len) *out_len = hst.final_len;
+  c->stats.decode_steps += hst.t;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev_begin, ev_end);
+  c->stats.last_generate_ms = ms;
+  cudaEventDestroy(ev_begin);
+  cudaEventDestroy(ev_end);
+  if (timing) {
+    double tot = 0;
+    int64_t bytes = 0;
+    size_t pairs = tm.next / 2;
+    int executed = hst.t;  // steps that actually did work
+    for (size_t i = 0; i < pairs; ++i) {
+      int step = (int)(i / g.n_layers);
+      if (step >= executed) break;
+      float e = 0.f;
+      cudaEventElapsedTime(&e, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]);
+      tot += e;
+      bytes += (int64_t)B * (step + 1) * 2 * I * (int64_t)sizeof(T);
+      c->stats.last_attn_launches = (int64_t)i + 1;
+    }
+    c->stats.last_attn_ms = tot;
+    c->stats.attn_bytes = bytes;
+  }
+  return 0;
+}
+
+template <typename T>
+static int generate_impl(m2m_ctx* c, const float* d_wave, const int64_t* d_cond, int B, int S, int max_length,
+                         int64_t* d_tokens, int* out_len, cudaStream_t s) {
+  const m2m_config& g = c->cfg;
+  if (out_len) *out_len = 1;
+  if (B == 0) return 0;
+  const int T_ = 1 + S / g.hop, L = T_ + g.n_cond;
+  // mel is written straight behind the conditioning rows? No: rows interleave per batch, so stage it.
+  DevBuf& mel = c->tf_x;  // reuse: [B, T, D] fp32
+  M2M_TRY(mel.ensure((size_t)B * T_ * g.d_model * sizeof(float), &c->generation));
+  M2M_TRY(c->embeds.ensure((size_t)B * L * g.d_model * sizeof(float), &c->generation));
+  M2M_TRY(logmel_impl(c, d_wave, B, S, mel.as<float>(), s));
+  M2M_TRY(condition_impl(c, mel.as<float>(), d_cond, B, T_, c->embeds.as<float>(), s));
+  return generate_from_embeds_impl<T>(c, c->embeds.as<float>(), B, L, max_length, nullptr, d_tokens, nullptr, out_len, s);
+}
+
+// ------------------------------------------------------------------ teacher-forced decoder (a10)
+template <typename T>
+static int decoder_forward_impl(m2m_ctx* c, const float* d_enc, int B, int L, const int64_t* d_dec_in, int Ld,
+                                float* d_logits, cudaStream_t s) {
+  const m2m_config& g = c->cfg;
+  M2M_REQUIRE(Ld >= 1 && Ld <= g.max_positions, "decoder length %d outside [1, %d]", Ld, g.max_positions);
+  M2M_REQUIRE(L >= 1 && L <= g.max_enc_len, "encoder length %d outside [1, %d]", L, g.max_enc_len);
+  if (B == 0) return 0;
+  const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
+  const size_t M = (size_t)B * Ld, Me = (size_t)B * L;
+  M2M_TRY(c->tf_x.ensure(M * D * sizeof(float), &c->generation));
+  M2M_TRY(c->tf_h.ensure(std::max(M, Me) * D * sizeof(T), &c->generation));
+  M2M_TRY(c->tf_qkv.ensure(M * 3 * I * sizeof(T), &c->generation));
+  M2M_TRY(c->tf_ao.ensure(M * I * sizeof(T), &c->generation));
+  M2M_TRY(c->tf_g.ensure(M * F * sizeof(T), &c->generation));
+  M2M_TRY(c->tf_q.ensure(M * I * sizeof(T), &c->generation));
+  float* x = c->tf_x.as<float>();
+  T* h = c->tf_h.as<T>();
+  T* qkv = c->tf_qkv.as<T>();
+  T* ao = c->tf_ao.as<T>();
+  T* gg = c->tf_g.as<T>();
+  T* q = c->tf_q.as<T>();
+  // typed copy of the encoder output, then cross K/V
+  {
+    size_t n4 = Me * D / 4;
+    unsigned blocks = (unsigned)std::min<size_t>((n4 + 255) / 256, 148 * 16);
+    cast_kernel<T><<<blocks, 256, 0, s>>>(d_enc, h, n4);
+    LAUNCH_CHECK(c);
+    M2M_TRY(cross_kv_impl<T>(c, h, B, L, s));
+  }
+  {
+    size_t total = M * (D / 4);
+    unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    embed_kernel<<<blocks, 256, 0, s>>>(d_dec_in, c->shared, x, M, D, V);
+    LAUNCH_CHECK(c);
+  }
+  for (int l = 0; l < g.n_layers; ++l) {
+    const DecLayerW& w = c->dec[l];
+    const T* ck = c->ckv.as<T>() + (size_t)l * Me * 2 * I;
+    M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, M, nullptr, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
+    M2M_TRY((seq_attn<T, true>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, 3 * I, ao, I, B, Ld, Ld, c->dec_bias_seq,
+                               2 * g.max_positions - 1, g.max_positions - 1, s)));
+    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
+    M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, M, nullptr, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, (int)M, I, D, EpiStore<T>{q, I}, nullptr, s));
+    M2M_TRY((seq_attn<T, false>(c, q, I, ck, ck + I, 2 * I, ao, I, B, Ld, L, nullptr, 0, 0, s)));
+    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
+    M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, M, nullptr, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));
+    M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, (int)M, D, F, EpiResidual{x, D}, nullptr, s));
+  }
+  M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, M, nullptr, s));
+  M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, (int)M, V, D, EpiStore<float>{d_logits, V}, nullptr, s));
+  return 0;
+}
+
+}  // namespace m2m
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+namespace m2m {
+
+static uint16_t f2bf(float f) {  // round-to-nearest-even, NaN preserved
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+struct ArenaBuilder {
+  std::vector<uint8_t> host;
+  size_t push_bytes(const void* p, size_t n) {
+    size_t off = align_up(host.size(), 256);
+    host.resize(off + n);
+    if (p) memcpy(host.data() + off, p, n);
+    return off;
+  }
+  size_t push_f32(const std::vector<float>& v) { return push_bytes(v.data(), v.size() * 4); }
+  size_t push_i32(const std::vector<int>& v) { return push_bytes(v.data(), v.size() * 4); }
+  size_t push_typed(const std::vector<float>& v, bool as_bf16) {
+    if (!as_bf16) return push_f32(v);
+    std::vector<uint16_t> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = f2bf(v[i]);
+    return push_bytes(h.data(), h.size() * 2);
+  }
+};
+
+static std::string normalize_key(const char* key) {
+  std::string k(key);
+  if (k.rfind("model.", 0) == 0) k = k.substr(6);  // Lightning checkpoint prefix (Music2MIDI.model)
+  return k;
+}
+
+static bool known_key(const m2m_config& g, const std::string& k) {
+  static const char* fixed[] = {"transformer.shared.weight", "transformer.encoder.embed_tokens.weight",
+                                "transformer.decoder.embed_tokens.weight", "transformer.encoder.final_layer_norm.weight",
+                                "transformer.decoder.final_layer_norm.weight", "transformer.lm_head.weight",
+                                "spectrogram.melspectrogram.spectrogram.window",
+                                "spectrogram.melspectrogram.mel_scale.fb"};
+  for (const char* f : fixed)
+    if (k == f) return true;
+  int i = 0;
+  char tail[128];
+  if (sscanf(k.c_str(), "conditioning.embeds.%d.%127s", &i, tail) == 2) return i >= 0 && i < g.n_cond && !strcmp(tail, "weight");
+  int l = 0, sub = 0;
+  char stack[16];
+  if (sscanf(k.c_str(), "transformer.%7[a-z].block.%d.layer.%d.%127s", stack, &l, &sub, tail) == 4) {
+    bool dec = !strcmp(stack, "decoder");
+    if (!dec && strcmp(stack, "encoder")) return false;
+    if (l < 0 || l >= g.n_layers) return false;
+    std::string t(tail);
+    const int ff = dec ? 2 : 1;
+    if (t == "layer_norm.weight") return sub >= 0 && sub <= ff;
+    if (sub == 0) {
+      if (t == "SelfAttention.relative_attention_bias.weight") return l == 0;
+      for (const char* n : {"q", "k", "v", "o"})
+        if (t == std::string("SelfAttention.") + n + ".weight") return true;
+    }
+    if (dec && sub == 1)
+      for (const char* n : {"q", "k", "v", "o"})
+        if (t == std::string("EncDecAttention.") + n + ".weight") return true;
+    if (sub == ff)
+      for (const char* n : {"wi_0", "wi_1", "wo"})
+        if (t == std::string("DenseReluDense.") + n + ".weight") return true;
+  }
+  return false;
+}
+
+static int get_staged(m2m_ctx* c, const std::string& key, size_t numel, const std::vector<float>** out) {
+  auto it = c->staged.find(key);
+  if (it == c->staged.end()) {
+    set_error("finalize: tensor '%s' was never set", key.c_str());
+    return M2M_ERR_STATE;
+  }
+  if (numel != 0 && it->second.size() != numel) {
+    set_error("finalize: tensor '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), numel);
+    return M2M_ERR_INVALID;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+static int ensure_device(m2m_ctx* c) { M2M_CUDA(cudaSetDevice(c->device)); return 0; }
+
+}  // namespace m2m
+
+extern "C" {
+
+int m2m_abi_version(void) { return M2M_ABI_VERSION; }
+const char* m2m_last_error(void) { return g_err; }
+
+int m2m_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+void m2m_default_config(m2m_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->n_layers = 6; cfg->d_model = 384; cfg->d_kv = 64; cfg->n_heads = 8; cfg->d_ff = 1152; cfg->vocab = 400;
+  cfg->n_buckets = 32; cfg->n_fft = 2048; cfg->hop = 256; cfg->n_cond = 2; cfg->max_positions = 1024;
+  cfg->max_enc_len = 512; cfg->pad_id = 0; cfg->bos_id = 1; cfg->eos_id = 2; cfg->precision = M2M_FP32;
+  cfg->ln_eps = 1e-6f;
+}
+
+int m2m_ctx_create(const m2m_config* cfg, int device, m2m_ctx** out) {
+  if (!cfg || !out) { set_error("null argument"); return M2M_ERR_INVALID; }
+  *out = nullptr;
+  const m2m_config& g = *cfg;
+  M2M_REQUIRE(g.d_kv == 64, "d_kv must be 64 (kernels are specialised for it), got %d", g.d_kv);
+  M2M_REQUIRE(g.n_heads > 0 && g.n_heads % 4 == 0, "n_heads must be a multiple of 4, got %d", g.n_heads);
+  M2M_REQUIRE(g.d_model % 128 == 0 && g.d_model <= 1024, "d_model must be a multiple of 128 and <= 1024, got %d", g.d_model);
+  M2M_REQUIRE(g.d_ff % 16 == 0 && g.vocab % 4 == 0 && g.n_fft % 16 == 0 && g.hop > 0, "unsupported d_ff/vocab/n_fft/hop");
+  M2M_REQUIRE(g.n_layers > 0 && g.n_cond >= 0 && g.n_cond <= 8 && g.max_positions >= 2 && g.max_enc_len >= 1, "bad sizes");
+  M2M_REQUIRE(g.precision == M2M_FP32 || g.precision == M2M_BF16, "unknown precision %d", g.precision);
+  M2M_REQUIRE(g.pad_id == 0, "pad_token_id must be 0");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); libm2m_b200 has no CPU fallback", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    return M2M_ERR_NO_DEVICE;
+  }
+  M2M_REQUIRE(device >= 0 && device < n, "device %d out of range [0, %d)", device, n);
+  cudaDeviceProp p;
+  M2M_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) {
+    set_error("device %d is sm_%d%d; libm2m_b200 is built for sm_100a (B200) only", device, p.major, p.minor);
+    return M2M_ERR_NO_DEVICE;
+  }
+  M2M_CUDA(cudaSetDevice(device));
+  m2m_ctx* c = new m2m_ctx();
+  c->cfg = g;
+  c->device = device;
+  c->num_sms = p.multiProcessorCount;
+  memset(&c->stats, 0, sizeof(c->stats));
+  if (cudaMallocHost((void**)&c->h_done, sizeof(int)) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->poll_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("context resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return M2M_ERR_CUDA;
+  }
+  *out = c;
+  return 0;
+}
+
+int m2m_ctx_destroy(m2m_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
+                    &c->enc_out, &c->ckv, &c->skv, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
+                    &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->tf_x, &c->tf_h,
+                    &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave, &c->host_cond, &c->host_tokens};
+  for (DevBuf* b : bufs) b->release();
+  if (c->h_done) cudaFreeHost(c->h_done);
+  if (c->poll_ev) cudaEventDestroy(c->poll_ev);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return 0;
+}
+
+int m2m_set_tensor(m2m_ctx* c, const char* key, const float* data, int64_t numel, int on_device) {
+  if (!c || !key || !data || numel <= 0) { set_error("m2m_set_tensor: bad argument"); return M2M_ERR_INVALID; }
+  std::string k = normalize_key(key);
+  M2M_REQUIRE(known_key(c->cfg, k), "m2m_set_tensor: unknown state-dict key '%s'", key);
+  std::vector<float>& v = c->staged[k];
+  v.resize((size_t)numel);
+  if (on_device) {
+    M2M_TRY(ensure_device(c));
+    M2M_CUDA(cudaMemcpy(v.data(), data, (size_t)numel * 4, cudaMemcpyDeviceToHost));
+  } else {
+    memcpy(v.data(), data, (size_t)numel * 4);
+  }
+  c->finalized = false;
+  return 0;
+}
+
+int m2m_set_bucket_luts(m2m_ctx* c, const int32_t* enc_lut, int enc_n, const int32_t* dec_lut, int dec_n) {
+  if (!c || !enc_lut || !dec_lut) { set_error("m2m_set_bucket_luts: null argument"); return M2M_ERR_INVALID; }
+  M2M_REQUIRE(enc_n % 2 == 1 && (enc_n - 1) / 2 >= c->cfg.max_enc_len - 1, "encoder bucket LUT too short: %d", enc_n);
+  M2M_REQUIRE(dec_n >= c->cfg.max_positions, "decoder bucket LUT too short: %d", dec_n);
+  for (int i = 0; i < enc_n; ++i) M2M_REQUIRE(enc_lut[i] >= 0 && enc_lut[i] < c->cfg.n_buckets, "bucket out of range");
+  for (int i = 0; i < dec_n; ++i) M2M_REQUIRE(dec_lut[i] >= 0 && dec_lut[i] < c->cfg.n_buckets, "bucket out of range");
+  c->enc_lut.assign(enc_lut, enc_lut + enc_n);
+  c->dec_lut.assign(dec_lut, dec_lut + dec_n);
+  c->finalized = false;
+  return 0;
+}
+
+int m2m_finalize_weights(m2m_ctx* c) {
+  if (!c) { set_error("null ctx"); return M2M_ERR_INVALID; }
+  M2M_TRY(ensure_device(c));
+  const m2m_config& g = c->cfg;
+  const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab, H = g.n_heads;
+  const bool bf = g.precision == M2M_BF16;
+  if (c->enc_lut.empty() || c->dec_lut.empty()) { set_error("finalize: bucket LUTs were never set"); return M2M_ERR_STATE; }
+  ArenaBuilder ab;
+  struct EncOff { size_t ln0, ln1, wqkv, wo, wi, wffo; };
+  struct DecOff { size_t ln0, ln1, ln2, wqkv, wo, wcq, wckv, wco, wi, wffo; };
+  std::vector<EncOff> eo(g.n_layers);
+  std::vector<DecOff> dof(g.n_layers);
+  const std::vector<float>* t = nullptr;
+  char key[256];
+
+  auto stack_rows = [&](const char* fmt, int l, std::initializer_list<const char*> names, size_t rows, size_t cols,
+                        std::vector<float>& out) -> int {
+    out.clear();
+    for (const char* n : names) {
+      snprintf(key, sizeof(key), fmt, l, n);
+      M2M_TRY(get_staged(c, key, rows * cols, &t));
+      out.insert(out.end(), t->begin(), t->end());
+    }
+    return 0;
+  };
+  auto interleave_wi = [&](const char* fmt, int l, std::vector<float>& out) -> int {
+    const std::vector<float>*a = nullptr, *b = nullptr;
+    snprintf(key, sizeof(key), fmt, l, "wi_0");
+    M2M_TRY(get_staged(c, key, (size_t)F * D, &a));
+    snprintf(key, sizeof(key), fmt, l, "wi_1");
+    M2M_TRY(get_staged(c, key, (size_t)F * D, &b));
+    out.resize((size_t)2 * F * D);
+    for (int j = 0; j < F; ++j) {
+      memcpy(&out[(size_t)(2 * j) * D], &(*a)[(size_t)j * D], D * 4);
+      memcpy(&out[(size_t)(2 * j + 1) * D], &(*b)[(size_t)j * D], D * 4);
+    }
+    return 0;
+  };
+  auto one = [&](const char* fmt, int l, const char* n, size_t numel, bool typed, size_t* off) -> int {
+    snprintf(key, sizeof(key), fmt, l, n);
+    M2M_TRY(get_staged(c, key, numel, &t));
+    *off = typed ? ab.push_typed(*t, bf) : ab.push_f32(*t);
+    return 0;
+  };
+
+  bool has_model = false;
+  for (auto& kv : c->staged)
+    if (kv.first.rfind("transformer.", 0) == 0) has_model = true;
+  size_t o_encfln = 0, o_decfln = 0, o_shared = 0, o_lm = 0, o_window = 0, o_encb = 0, o_decb = 0, o_decbs = 0;
+  const int n_freq = g.n_fft / 2 + 1;
+  const int enc_ld = 2 * g.max_enc_len - 1, enc_c = ((int)c->enc_lut.size() - 1) / 2;
+  M2M_TRY(get_staged(c, "spectrogram.melspectrogram.spectrogram.window", g.n_fft, &t)); o_window = ab.push_f32(*t);
+  if (has_model) {
+  std::vector<float> tmp;
+  for (int l = 0; l < g.n_layers; ++l) {
+    M2M_TRY(one("transformer.encoder.block.%d.layer.0.%s.weight", l, "layer_norm", D, false, &eo[l].ln0));
+    M2M_TRY(stack_rows("transformer.encoder.block.%d.layer.0.SelfAttention.%s.weight", l, {"q", "k", "v"}, I, D, tmp));
+    eo[l].wqkv = ab.push_typed(tmp, bf);
+    M2M_TRY(one("transformer.encoder.block.%d.layer.0.SelfAttention.%s.weight", l, "o", (size_t)D * I, true, &eo[l].wo));
+    M2M_TRY(one("transformer.encoder.block.%d.layer.1.%s.weight", l, "layer_norm", D, false, &eo[l].ln1));
+    M2M_TRY(interleave_wi("transformer.encoder.block.%d.layer.1.DenseReluDense.%s.weight", l, tmp));
+    eo[l].wi = ab.push_typed(tmp, bf);
+    M2M_TRY(one("transformer.encoder.block.%d.layer.1.DenseReluDense.%s.weight", l, "wo", (size_t)D * F, true, &eo[l].wffo));
+
+    M2M_TRY(one("transformer.decoder.block.%d.layer.0.%s.weight", l, "layer_norm", D, false, &dof[l].ln0));
+    M2M_TRY(stack_rows("transformer.decoder.block.%d.layer.0.SelfAttention.%s.weight", l, {"q", "k", "v"}, I, D, tmp));
+    dof[l].wqkv = ab.push_typed(tmp, bf);
+    M2M_TRY(one("transformer.decoder.block.%d.layer.0.SelfAttention.%s.weight", l, "o", (size_t)D * I, true, &dof[l].wo));
+    M2M_TRY(one("transformer.decoder.block.%d.layer.1.%s.weight", l, "layer_norm", D, false, &dof[l].ln1));
+    M2M_TRY(one("transformer.decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, "q", (size_t)I * D, true, &dof[l].wcq));
+    M2M_TRY(stack_rows("transformer.decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, {"k", "v"}, I, D, tmp));
+    dof[l].wckv = ab.push_typed(tmp, bf);
+    M2M_TRY(one("transformer.decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, "o", (size_t)D * I, true, &dof[l].wco));
+    M2M_TRY(one("transformer.decoder.block.%d.layer.2.%s.weight", l, "layer_norm", D, false, &dof[l].ln2));
+    M2M_TRY(interleave_wi("transformer.decoder.block.%d.layer.2.DenseReluDense.%s.weight", l, tmp));
+    dof[l].wi = ab.push_typed(tmp, bf);
+    M2M_TRY(one("transformer.decoder.block.%d.layer.2.DenseReluDense.%s.weight", l, "wo", (size_t)D * F, true, &dof[l].wffo));
+  }
+  M2M_TRY(get_staged(c, "transformer.encoder.final_layer_norm.weight", D, &t)); o_encfln = ab.push_f32(*t);
+  M2M_TRY(get_staged(c, "transformer.decoder.final_layer_norm.weight", D, &t)); o_decfln = ab.push_f32(*t);
+  M2M_TRY(get_staged(c, "transformer.shared.weight", (size_t)V * D, &t)); o_shared = ab.push_f32(*t);
+  M2M_TRY(get_staged(c, "transformer.lm_head.weight", (size_t)V * D, &t)); o_lm = ab.push_typed(*t, bf);
+
+  // relative-position bias LUTs (block 0 tables, shared by all blocks)
+  std::vector<float> enc_bias((size_t)H * enc_ld), dec_bias((size_t)H * g.max_positions),
+      dec_bias_seq((size_t)H * (2 * g.max_positions - 1));
+  M2M_TRY(get_staged(c, "transformer.encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
+                     (size_t)g.n_buckets * H, &t));
+  for (int h = 0; h < H; ++h)
+    for (int i = 0; i < enc_ld; ++i) {
+      int rel = i - (g.max_enc_len - 1);
+      enc_bias[(size_t)h * enc_ld + i] = (*t)[(size_t)c->enc_lut[rel + enc_c] * H + h];
+    }
+  M2M_TRY(get_staged(c, "transformer.decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
+                     (size_t)g.n_buckets * H, &t));
+  for (int h = 0; h < H; ++h) {
+    for (int d = 0; d < g.max_positions; ++d) dec_bias[(size_t)h * g.max_positions + d] = (*t)[(size_t)c->dec_lut[d] * H + h];
+    for (int i = 0; i < 2 * g.max_positions - 1; ++i) {
+      int rel = i - (g.max_positions - 1);  // key - query; rel > 0 is masked, HF maps it to bucket(0)
+      dec_bias_seq[(size_t)h * (2 * g.max_positions - 1) + i] = (*t)[(size_t)c->dec_lut[rel < 0 ? -rel : 0] * H + h];
+    }
+  }
+  o_encb = ab.push_f32(enc_bias); o_decb = ab.push_f32(dec_bias); o_decbs = ab.push_f32(dec_bias_seq);
+
+  }  // has_model
+
+  // DFT basis, rows interleaved (2f = cos, 2f+1 = sin), exact integer angle reduction, fp64 -> fp32
+  const int dft_rows = (int)align_up((size_t)2 * n_freq, 4);
+  std::vector<float> basis((size_t)dft_rows * g.n_fft, 0.f);
+  {
+    std::vector<double> ct(g.n_fft), stb(g.n_fft);
+    for (int r = 0; r < g.n_fft; ++r) {
+      double a = 2.0 * M_PI * (double)r / (double)g.n_fft;
+      ct[r] = cos(a);
+      stb[r] = sin(a);
+    }
+    for (int f = 0; f < n_freq; ++f)
+      for (int k = 0; k < g.n_fft; ++k) {
+        int r = (int)(((long long)f * k) % g.n_fft);
+        basis[(size_t)(2 * f) * g.n_fft + k] = (float)ct[r];
+        basis[(size_t)(2 * f + 1) * g.n_fft + k] = (float)stb[r];
+      }
+  }
+  size_t o_basis = ab.push_f32(basis);
+  basis.clear();
+  basis.shrink_to_fit();
+
+  // banded mel filterbank
+  M2M_TRY(get_staged(c, "spectrogram.melspectrogram.mel_scale.fb", (size_t)n_freq * D, &t));
+  std::vector<int> bstart(D, 0), blen(D, 0);
+  std::vector<float> bw((size_t)D * c->max_band, 0.f);
+  for (int j = 0; j < D; ++j) {
+    int first = -1, last = -1;
+    for (int f = 0; f < n_freq; ++f)
+      if ((*t)[(size_t)f * D + j] != 0.f) {
+        if (first < 0) first = f;
+        last = f;
+      }
+    if (first < 0) continue;
+    int n = last - first + 1;
+    if (n > c->max_band) {
+      set_error("finalize: mel filter %d spans %d bins (> %d); only banded filterbanks are supported", j, n, c->max_band);
+      return M2M_ERR_INVALID;
+    }
+    bstart[j] = first;
+    blen[j] = n;
+    for (int i = 0; i < n; ++i) bw[(size_t)j * c->max_band + i] = (*t)[(size_t)(first + i) * D + j];
+  }
+  size_t o_bs = ab.push_i32(bstart), o_bl = ab.push_i32(blen), o_bw = ab.push_f32(bw);
+
+  // conditioning tables, concatenated
+  std::vector<float> cemb;
+  std::vector<int> coff(std::max(1, g.n_cond), 0), crows(std::max(1, g.n_cond), 0);
+  for (int i = 0; i < g.n_cond; ++i) {
+    snprintf(key, sizeof(key), "conditioning.embeds.%d.weight", i);
+    if (!has_model && c->staged.find(key) == c->staged.end()) continue;
+    M2M_TRY(get_staged(c, key, 0, &t));
+    M2M_REQUIRE(t->size() % D == 0, "finalize: '%s' is not a multiple of d_model", key);
+    coff[i] = (int)(cemb.size() / D);
+    crows[i] = (int)(t->size() / D);
+    cemb.insert(cemb.end(), t->begin(), t->end());
+  }
+  if (cemb.empty()) cemb.resize(D, 0.f);
+  size_t o_cemb = ab.push_f32(cemb), o_coff = ab.push_i32(coff), o_crows = ab.push_i32(crows);
+
+  M2M_CUDA(cudaDeviceSynchronize());
+  M2M_TRY(c->arena.ensure(ab.host.size(), &c->generation));
+  M2M_CUDA(cudaMemcpy(c->arena.p, ab.host.data(), ab.host.size(), cudaMemcpyHostToDevice));
+  uint8_t* base = c->arena.as<uint8_t>();
+  auto F32 = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  c->enc.resize(g.n_layers);
+  c->dec.resize(g.n_layers);
+  for (int l = 0; l < g.n_layers && has_model; ++l) {
+    c->enc[l] = EncLayerW{F32(eo[l].ln0), F32(eo[l].ln1), base + eo[l].wqkv, base + eo[l].wo, base + eo[l].wi,
+                          base + eo[l].wffo};
+    c->dec[l] = DecLayerW{F32(dof[l].ln0), F32(dof[l].ln1), F32(dof[l].ln2), base + dof[l].wqkv, base + dof[l].wo,
+                          base + dof[l].wcq, base + dof[l].wckv, base + dof[l].wco, base + dof[l].wi, base + dof[l].wffo};
+  }
+  c->enc_final_ln = F32(o_encfln);
+  c->dec_final_ln = F32(o_decfln);
+  c->shared = F32(o_shared);
+  c->lm_head = base + o_lm;
+  c->window = F32(o_window);
+  c->enc_bias = F32(o_encb);
+  c->enc_bias_ld = enc_ld;
+  c->dec_bias = F32(o_decb);
+  c->dec_bias_seq = F32(o_decbs);
+  c->dft_basis = F32(o_basis);
+  c->dft_rows = dft_rows;
+  c->n_freq = n_freq;
+  c->band_start = reinterpret_cast<int*>(base + o_bs);
+  c->band_len = reinterpret_cast<int*>(base + o_bl);
+  c->band_w = F32(o_bw);
+  c->cond_emb = F32(o_cemb);
+  c->cond_off = reinterpret_cast<int*>(base + o_coff);
+  c->cond_rows = reinterpret_cast<int*>(base + o_crows);
+  c->finalized = true;
+  c->model_ready = has_model;
+  return 0;
+}
+
+#define M2M_ENTER(c)                                                                 \
+  if (!(c)) { set_error("null ctx"); return M2M_ERR_INVALID; }                       \
+  if (!(c)->finalized) { set_error("weights not finalised (m2m_finalize_weights)"); return M2M_ERR_STATE; } \
+  M2M_TRY(ensure_device(c));                                                         \
+  cudaStream_t s = (cudaStream_t)stream;
+#define M2M_NEED_MODEL(c) \
+  if (!(c)->model_ready) { set_error("this context holds only the log-mel frontend (no transformer weights were set)"); return M2M_ERR_STATE; }
+
+int m2m_logmel(m2m_ctx* c, const float* d_wave, int B, int S, float* d_mel, void* stream) {
+  M2M_ENTER(c);
+  return logmel_impl(c, d_wave, B, S, d_mel, s);
+}
+
+int m2m_condition(m2m_ctx* c, const float* d_feature, const int64_t* d_cond, int B, int T, float* d_embeds, void* stream) {
+  M2M_ENTER(c);
+  return condition_impl(c, d_feature, d_cond, B, T, d_embeds, s);
+}
+
+int m2m_encode(m2m_ctx* c, const float* d_embeds, int B, int L, float* d_out, void* stream) {
+  M2M_ENTER(c);
+  M2M_NEED_MODEL(c);
+  return c->cfg.precision == M2M_BF16 ? encode_impl<bf16>(c, d_embeds, B, L, d_out, false, s)
+                                      : encode_impl<float>(c, d_embeds, B, L, d_out, false, s);
+}
+
+int m2m_generate_from_embeds(m2m_ctx* c, const float* d_embeds, int B, int L, int max_length, const int64_t* d_forced,
+                             int64_t* d_tokens, float* d_logits, int* out_len, void* stream) {
+  M2M_ENTER(c);
+  M2M_NEED_MODEL(c);
+  return c->cfg.precision == M2M_BF16
+             ? generate_from_embeds_impl<bf16>(c, d_embeds, B, L, max_length, d_forced, d_tokens, d_logits, out_len, s)
+             : generate_from_embeds_impl<float>(c, d_embeds, B, L, max_length, d_forced, d_tokens, d_logits, out_len, s);
+}
+
+int m2m_generate(m2m_ctx* c, const float* d_wave, const int64_t* d_cond, int B, int S, int max_length, int64_t* d_tokens,
+                 int* out_len, void* stream) {
+  M2M_ENTER(c);
+  M2M_NEED_MODEL(c);
+  return c->cfg.precision == M2M_BF16 ? generate_impl<bf16>(c, d_wave, d_cond, B, S, max_length, d_tokens, out_len, s)
+                                      : generate_impl<float>(c, d_wave, d_cond, B, S, max_length, d_tokens, out_len, s);
+}
+
+int m2m_decoder_forward(m2m_ctx* c, const float* d_enc, int B, int L, const int64_t* d_dec_in, int Ld, float* d_logits,
+                        void* stream) {
+  M2M_ENTER(c);
+  M2M_NEED_MODEL(c);
+  return c->cfg.precision == M2M_BF16 ? decoder_forward_impl<bf16>(c, d_enc, B, L, d_dec_in, Ld, d_logits, s)
+                                      : decoder_forward_impl<float>(c, d_enc, B, L, d_dec_in, Ld, d_logits, s);
+}
+
+int m2m_transcribe_host(m2m_ctx* c, const float* h_wave, int64_t n_seg, int S, const int64_t* h_cond, int max_length,
+                        int device_batch, int64_t* h_tokens, int32_t* h_lens) {
+  void* stream = c ? (void*)c->own_stream : nullptr;
+  M2M_ENTER(c);
+  M2M_NEED_MODEL(c);
+  M2M_REQUIRE(n_seg >= 0 && device_batch > 0 && h_wave && h_tokens, "m2m_transcribe_host: bad argument");
+  const int nc = c->cfg.n_cond;
+  for (int64_t i0 = 0; i0 < n_seg; i0 += device_batch) {
+    int nb = (int)std::min<int64_t>(device_batch, n_seg - i0);
+    M2M_TRY(c->host_wave.ensure((size_t)nb * S * sizeof(float), &c->generation));
+    M2M_TRY(c->host_cond.ensure((size_t)nb * std::max(1, nc) * sizeof(int64_t), &c->generation));
+    M2M_TRY(c->host_tokens.ensure((size_t)nb * max_length * sizeof(int64_t), &c->generation));
+    M2M_CUDA(cudaMemcpyAsync(c->host_wave.p, h_wave + (size_t)i0 * S, (size_t)nb * S * sizeof(float),
+                             cudaMemcpyHostToDevice, s));
+    if (h_cond)
+      M2M_CUDA(cudaMemcpyAsync(c->host_cond.p, h_cond + (size_t)i0 * nc, (size_t)nb * nc * sizeof(int64_t),
+                               cudaMemcpyHostToDevice, s));
+    else
+      M2M_CUDA(cudaMemsetAsync(c->host_cond.p, 0, (size_t)nb * std::max(1, nc) * sizeof(int64_t), s));
+    int len = 0;
+    int rc = c->cfg.precision == M2M_BF16
+                 ? generate_impl<bf16>(c, c->host_wave.as<float>(), c->host_cond.as<int64_t>(), nb, S, max_length,
+                                       c->host_tokens.as<int64_t>(), &len, s)
+                 : generate_impl<float>(c, c->host_wave.as<float>(), c->host_cond.as<int64_t>(), nb, S, max_length,
+                                        c->host_tokens.as<int64_t>(), &len, s);
+    if (rc) return rc;
+    M2M_CUDA(cudaMemcpyAsync(h_tokens + (size_t)i0 * max_length, c->host_tokens.p,
+                             (size_t)nb * max_length * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    M2M_CUDA(cudaStreamSynchronize(s));
+  }
+  if (h_lens)
+    for (int64_t i = 0; i < n_seg; ++i) {
+      const int64_t* r = h_tokens + (size_t)i * max_length;
+      int n = max_length;
+      for (int j = 0; j < max_length; ++j)
+        if (r[j] == c->cfg.eos_id) { n = j + 1; break; }
+      h_lens[i] = n;
+    }
+  return 0;
+}
+
+int m2m_stats_reset(m2m_ctx* c) {
+  if (!c) return M2M_ERR_INVALID;
+  memset(&c->stats, 0, sizeof(c->stats));
+  return 0;
+}
+int m2m_stats_get(m2m_ctx* c, m2m_stats* out) {
+  if (!c || !out) return M2M_ERR_INVALID;
+  *out = c->stats;
+  return 0;
+}
+int m2m_set_flags(m2m_ctx* c, uint32_t flags) {
+  if (!c) return M2M_ERR_INVALID;
+  c->flags = flags;
+  return 0;
+}
+
+}  // extern "C"

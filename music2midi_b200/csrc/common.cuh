@@ -1,0 +1,142 @@
+// Shared helpers for libm2m_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/m2m_b200.h"
+
+namespace m2m {
+
+typedef __nv_bfloat16 bf16;
+
+void set_error(const char* fmt, ...);
+
+#define M2M_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      m2m::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return M2M_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define M2M_TRY(expr)       \
+  do {                      \
+    int _s = (expr);        \
+    if (_s != 0) return _s; \
+  } while (0)
+
+#define M2M_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      m2m::set_error(__VA_ARGS__);  \
+      return M2M_ERR_INVALID;       \
+    }                               \
+  } while (0)
+
+// Decode-loop state, resident in device memory; every kernel of the captured decode step reads
+// it instead of taking step-dependent launch arguments, so ONE CUDA graph serves all steps.
+struct DecState {
+  int t;            // number of tokens already in the self-attention cache == current step
+  int done;         // all rows finished (or length cap reached): remaining launches are no-ops
+  int final_len;    // output length (HF dynamic length), valid when done
+  int unfinished;   // rows still unfinished after the current step (accumulated by atomics)
+  int max_length;   // length cap
+  int pad_[3];
+};
+
+// ---- conversions ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// load 4 consecutive elements as floats (16 B for float, 8 B for bf16); pointer suitably aligned
+__device__ __forceinline__ void load4(const float* p, float o[4]) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float o[4]) {
+  uint2 v = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&v.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  o[0] = fa.x; o[1] = fa.y; o[2] = fb.x; o[3] = fb.y;
+}
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float v[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// 16-byte vector of T as floats: 4 floats or 8 bf16
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* o) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec16<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float* o) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // bf16 -> f32 is a 16-bit shift
+      o[2 * i] = __uint_as_float(w[i] << 16);
+      o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&a);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// gelu_new (tanh approximation), transformers NewGELUActivation
+__device__ __forceinline__ float gelu_new(float x) {
+  const float k = 0.7978845608028654f;  // sqrt(2/pi)
+  return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * (x * x * x))));
+}
+
+}  // namespace m2m

@@ -1,0 +1,365 @@
+// Non-GEMM kernels of the hot path: norms, gathers, attention (encoder, KV-cached decode),
+// greedy token selection, banded mel + log.  All HBM/latency-bound: coalesced 16-byte accesses,
+// warp-level reductions, no tensor cores (a decode query is a GEMV: no operand reuse).
+#pragma once
+
+#include <math.h>
+
+#include "common.cuh"
+
+namespace m2m {
+
+// ------------------------------------------------------------------ T5 RMSNorm (a7)
+// y = w * (x * rsqrt(mean(x^2) + eps));  one warp per row, D % 128 == 0, D <= 1024.
+template <typename TO>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      TO* __restrict__ y, int rows, int D, float eps,
+                                                      const DecState* __restrict__ st) {
+  if (st != nullptr && st->done) return;
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  const float* xr = x + (size_t)row * D;
+  float v[8][4];
+  float ss = 0.f;
+  int nv = D >> 7;  // float4 per lane
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < nv) {
+      load4(xr + (i * 32 + lane) * 4, v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss += v[i][e] * v[i][e];
+    }
+  }
+  ss = warp_sum(ss);
+  float rstd = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < nv) {
+      float wv[4], o[4];
+      load4(w + (i * 32 + lane) * 4, wv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = wv[e] * (v[i][e] * rstd);
+      store4(y + (size_t)row * D + (i * 32 + lane) * 4, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ conditioning (a4)
+// out[b, 0..n_cond) = embeds[i][cond[b,i]];  out[b, n_cond + t] = feature[b, t]
+__global__ void condition_kernel(const float* __restrict__ feat, const int64_t* __restrict__ cond,
+                                 const float* __restrict__ emb, const int* __restrict__ emb_row_off,
+                                 const int* __restrict__ emb_rows, float* __restrict__ out, int B, int T, int D,
+                                 int n_cond, int* __restrict__ err) {
+  int L = T + n_cond;
+  size_t total = (size_t)B * L * (D / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int d4 = i % (D / 4);
+    size_t r = i / (D / 4);
+    int l = r % L;
+    int b = r / L;
+    float4 v;
+    if (l < n_cond) {
+      long idx = cond[(size_t)b * n_cond + l];
+      if (idx < 0 || idx >= emb_rows[l]) {  // nn.Embedding raises IndexError; report, clamp
+        *err = 1;
+        idx = 0;
+      }
+      v = reinterpret_cast<const float4*>(emb + ((size_t)emb_row_off[l] + idx) * D)[d4];
+    } else {
+      v = reinterpret_cast<const float4*>(feat + ((size_t)b * T + (l - n_cond)) * D)[d4];
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+// token embedding rows -> fp32 residual stream x[r, :] = shared[tok[r], :]
+__global__ void embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table, float* __restrict__ x,
+                             size_t rows, int D, int vocab) {
+  size_t total = rows * (D / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / (D / 4);
+    int d4 = i % (D / 4);
+    long t = tok[r];
+    t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);
+    reinterpret_cast<float4*>(x)[i] = reinterpret_cast<const float4*>(table + (size_t)t * D)[d4];
+  }
+}
+
+// ------------------------------------------------------------------ full-sequence attention (a7, a10)
+// One block per (query tile, head, batch).  qkv rows are (b, l) with columns [q | k | v] or separate
+// pointers with their own leading dimensions.  scores = q.k + bias[h][(j - i) + bias_zero] (+ causal
+// mask), fp32 softmax, out = P V.  K/V of the (b, h) pair are staged in shared memory as fp32.
+// No 1/sqrt(d) scaling (T5).  d_kv == 64.
+template <typename T, bool CAUSAL>
+__global__ void __launch_bounds__(256) seq_attn_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K,
+                                                       const T* __restrict__ V, int ldkv, T* __restrict__ O, int ldo,
+                                                       int Lq, int Lk, const float* __restrict__ bias, int bias_ld,
+                                                       int bias_zero, int q_tile) {
+  extern __shared__ __align__(16) float smem[];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * q_tile;
+  const int q1 = min(Lq, q0 + q_tile);
+  const int nk = CAUSAL ? min(Lk, q1) : Lk;  // keys needed by this query tile
+  float* Ks = smem;                  // [nk][65]
+  float* Vs = Ks + (size_t)Lk * 65;  // [nk][64]
+  float* Ps = Vs + (size_t)Lk * 64;  // [8 warps][Lk]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < nk * 16; i += 256) {
+    int j = i >> 4, c = (i & 15) * 4;
+    float kv[4], vv[4];
+    load4(K + ((size_t)b * Lk + j) * ldkv + h * 64 + c, kv);
+    load4(V + ((size_t)b * Lk + j) * ldkv + h * 64 + c, vv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      Ks[j * 65 + c + e] = kv[e];
+      Vs[j * 64 + c + e] = vv[e];
+    }
+  }
+  __syncthreads();
+
+  float* P = Ps + (size_t)warp * Lk;
+  for (int i = q0 + warp; i < q1; i += 8) {
+    float q[64];
+    const T* qp = Q + ((size_t)b * Lq + i) * ldq + h * 64;
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) load4(qp + c, q + c);
+    const int lim = CAUSAL ? i + 1 : nk;
+    float mx = -INFINITY;
+    for (int j = lane; j < lim; j += 32) {
+      const float* kr = Ks + j * 65;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) s = fmaf(q[d], kr[d], s);
+      if (bias != nullptr) s += bias[(size_t)h * bias_ld + (j - i) + bias_zero];
+      P[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < lim; j += 32) {
+      float p = expf(P[j] - mx);
+      P[j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float inv = 1.f / sum;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < lim; ++j) {
+      float p = P[j] * inv;  // HF normalises the weights before the PV product
+      o0 = fmaf(p, Vs[j * 64 + lane], o0);
+      o1 = fmaf(p, Vs[j * 64 + lane + 32], o1);
+    }
+    T* op = O + ((size_t)b * Lq + i) * ldo + h * 64;
+    op[lane] = from_f<T>(o0);
+    op[lane + 32] = from_f<T>(o1);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ KV-cached decode attention (a8)
+// One warp per (row b, head h); a block is 4 warps = 4 heads of one row; grid = (H/4, B).
+// Cache layout [b][j][h][64] (key stride `key_stride` elements, batch stride `row_stride`): every key of a (b, h) pair is one 128 B (bf16) / 256 B (fp32) line,
+// read with 16-byte loads (LPK lanes per key), perfectly coalesced.  Online softmax per key slot,
+// slots merged with shuffles at the end: K and V are each read exactly once.
+//   SELF:  nkeys = st->t + 1 (the current token's K/V were written by the QKV GEMM epilogue),
+//          score += bias[h][t - j]   (decoder unidirectional bucket LUT, block 0's table)
+//   CROSS: nkeys fixed (encoder length), no bias.
+template <typename T, bool SELF, bool FAST_EXP>
+__global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ q, const T* __restrict__ Kc,
+                                                          const T* __restrict__ Vc, size_t row_stride, int key_stride,
+                                                          int nkeys_fixed,
+                                                          const float* __restrict__ bias, int bias_ld,
+                                                          T* __restrict__ out, int H,
+                                                          const DecState* __restrict__ st,
+                                                          const uint8_t* __restrict__ finished) {
+  if (st->done) return;
+  const int b = blockIdx.y;
+  if (finished != nullptr && finished[b]) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * 4 + warp;
+  const int inner = H * 64;
+  constexpr int VEC = Vec16<T>::N;     // elements per 16 B
+  constexpr int LPK = 64 / VEC;        // lanes per key
+  constexpr int KPI = 32 / LPK;        // keys per warp-wide load
+  constexpr int U = 4;                 // unroll: U*KPI keys in flight per warp
+  const int g = lane / LPK, c = lane % LPK;
+  const int t = st->t;
+  const int nkeys = SELF ? t + 1 : nkeys_fixed;
+
+  float qv[VEC];
+  Vec16<T>::load(q + (size_t)b * inner + h * 64 + c * VEC, qv);
+  const T* kb = Kc + (size_t)b * row_stride + h * 64 + c * VEC;
+  const T* vb = Vc + (size_t)b * row_stride + h * 64 + c * VEC;
+  const float* bh = SELF ? bias + (size_t)h * bias_ld : nullptr;
+
+  float m = -INFINITY, l = 0.f, acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+
+  for (int j0 = 0; j0 < nkeys; j0 += KPI * U) {
+    float kv[U][VEC], vv[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int j = j0 + u * KPI + g;
+      if (j < nkeys) {
+        Vec16<T>::load(kb + (size_t)j * key_stride, kv[u]);
+        Vec16<T>::load(vb + (size_t)j * key_stride, vv[u]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) kv[u][e] = vv[u][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int j = j0 + u * KPI + g;
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) s = fmaf(qv[e], kv[u][e], s);
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (j < nkeys) {
+        if (SELF) s += __ldg(bh + (t - j));
+        float mn = fmaxf(m, s);
+        float sc = FAST_EXP ? __expf(m - mn) : expf(m - mn);  // m = -inf -> 0
+        float p = FAST_EXP ? __expf(s - mn) : expf(s - mn);
+        l = l * sc + p;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * sc + p * vv[u][e];
+        m = mn;
+      }
+    }
+  }
+  // merge the KPI key slots
+#pragma unroll
+  for (int o = LPK; o < 32; o <<= 1) {
+    float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    float mn = fmaxf(m, m2);
+    float s1 = (m == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m - mn) : expf(m - mn));
+    float s2 = (m2 == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m2 - mn) : expf(m2 - mn));
+    l = l * s1 + l2 * s2;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float a2 = __shfl_xor_sync(0xffffffffu, acc[e], o);
+      acc[e] = acc[e] * s1 + a2 * s2;
+    }
+    m = mn;
+  }
+  if (g == 0) {
+    float inv = 1.f / l;
+    float o[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) o[e] = acc[e] * inv;
+    Vec16<T>::store(out + (size_t)b * inner + h * 64 + c * VEC, o);
+  }
+}
+
+// torch.argmax order: NaN beats everything, then larger value, then lower index.
+__device__ __forceinline__ bool argmax_better(float v, int i, float best, int bi) {
+  if (i == 0x7fffffff) return false;
+  if (bi == 0x7fffffff) return true;
+  bool vn = v != v, bn = best != best;
+  if (vn != bn) return vn;
+  if (vn) return i < bi;
+  return v > best || (v == best && i < bi);
+}
+
+// ------------------------------------------------------------------ greedy selection (a9)
+// One block per row: argmax (lowest index wins ties, NaN counts as max like torch.argmax),
+// pad-if-finished, EOS bookkeeping, optional teacher forcing, next-step embedding gather.
+__global__ void __launch_bounds__(128) select_token_kernel(const float* __restrict__ logits, int V,
+                                                           int64_t* __restrict__ tokens, int ld_tok,
+                                                           const int64_t* __restrict__ forced,
+                                                           uint8_t* __restrict__ finished,
+                                                           const float* __restrict__ table, float* __restrict__ x, int D,
+                                                           float* __restrict__ logits_out, DecState* __restrict__ st,
+                                                           int pad_id, int eos_id) {
+  if (st->done) return;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int t = st->t;
+  const float* lr = logits + (size_t)b * V;
+  float best = 0.f;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < V; i += 128) {
+    float v = lr[i];
+    if (logits_out != nullptr) logits_out[((size_t)b * (st->max_length - 1) + t) * V + i] = v;
+    if (argmax_better(v, i, best, bi)) { best = v; bi = i; }
+  }
+  __shared__ float sv[128];
+  __shared__ int si[128];
+  sv[tid] = best;
+  si[tid] = bi;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (tid < s && argmax_better(sv[tid + s], si[tid + s], sv[tid], si[tid])) {
+      sv[tid] = sv[tid + s];
+      si[tid] = si[tid + s];
+    }
+    __syncthreads();
+  }
+  __shared__ int s_next;
+  if (tid == 0) {
+    int fin = finished[b];
+    int next = fin ? pad_id : si[0];
+    if (forced != nullptr) next = (int)forced[(size_t)b * ld_tok + t + 1];
+    tokens[(size_t)b * ld_tok + t + 1] = next;
+    if (next == eos_id) fin = 1;
+    finished[b] = (uint8_t)fin;
+    if (!fin) atomicAdd(&st->unfinished, 1);
+    s_next = next < 0 ? 0 : (next >= V ? V - 1 : next);
+  }
+  __syncthreads();
+  const float4* src = reinterpret_cast<const float4*>(table + (size_t)s_next * D);
+  float4* dst = reinterpret_cast<float4*>(x + (size_t)b * D);
+  for (int i = tid; i < D / 4; i += 128) dst[i] = src[i];
+}
+
+// advances the step counter; detects "all rows finished" / length cap.  <<<1,1>>>
+__global__ void step_advance_kernel(DecState* st, int greedy_stop) {
+  if (st->done) return;
+  int t = st->t + 1;  // tokens generated so far = t (excluding BOS) -> sequence length t + 1
+  st->t = t;
+  if ((greedy_stop && st->unfinished == 0) || t + 1 >= st->max_length) {
+    st->done = 1;
+    st->final_len = t + 1;
+  }
+  st->unfinished = 0;
+}
+
+// ------------------------------------------------------------------ banded mel + clamp + log (a3)
+// out[m, j] = log(max(sum_i P[m, start[j] + i] * w[j][i], 1e-6)); the HTK filterbank is 0.5 % dense
+// (<= 14 taps per filter), so the projection is a banded gather, not a GEMM.
+__global__ void __launch_bounds__(128) mel_band_log_kernel(const float* __restrict__ P, int ldp,
+                                                           const int* __restrict__ start, const int* __restrict__ len,
+                                                           const float* __restrict__ w, int max_band,
+                                                           float* __restrict__ out, size_t rows, int n_mels) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_mels) return;
+  int s = start[j], n = len[j];
+  float wv[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) wv[i] = (i < n) ? w[(size_t)j * max_band + i] : 0.f;
+  for (size_t m = blockIdx.y; m < rows; m += gridDim.y) {
+    const float* pr = P + m * ldp + s;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n) acc = fmaf(__ldg(pr + i), wv[i], acc);
+    out[m * n_mels + j] = logf(fmaxf(acc, 1e-6f));
+  }
+}
+
+// fp32 -> T copy (n4 = number of 4-element groups)
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float v[4];
+    load4(in + i * 4, v);
+    store4(out + i * 4, v);
+  }
+}
+
+}  // namespace m2m

@@ -1,0 +1,148 @@
+"""Application model: audio in, MIDI out.
+
+Drop-in for the inference surface of the reference's ``music2midi/model.py`` (``Music2MIDI``:
+``__init__(config_path)``, ``generate`` :67-99, ``sample_tokens`` :101-140, ``evaluate_batch`` :55-65,
+``load_from_checkpoint``, ``.model/.config/.device``).  The reference class is a
+``pl.LightningModule``; training (``training_step``/``configure_optimizers``, :27-53) is out of scope
+here, so this is a plain ``nn.Module`` that understands Lightning checkpoint files.
+
+Differences that do not change results: segments are independent, so instead of
+chunks of ``inference.batch_size`` (=128) the B200 path decodes ``inference.device_batch_size``
+segments at a time, and on several GPUs clips are sharded across ranks (music2midi_b200/distributed.py).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .config import load_config
+from .input import ModelInputs
+from .transformer import T5Transformer
+from .utils import numpy_to_midi
+
+
+def load_audio(path: Union[str, Path], sr: int) -> np.ndarray:
+    """Mono float32 at ``sr`` Hz (the reference calls ``librosa.load(path, sr=sr)``, model.py:84)."""
+    try:
+        import librosa  # type: ignore
+
+        return librosa.load(str(path), sr=sr)[0]
+    except ImportError:
+        pass
+    import wave as _wave
+
+    from scipy.signal import resample_poly
+
+    with _wave.open(str(path), "rb") as f:
+        n_ch, width, rate, n = f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()
+        raw = f.readframes(n)
+    if width == 2:
+        y = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+    elif width == 4:
+        y = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+    elif width == 1:
+        y = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    else:
+        raise ValueError(f"unsupported WAV sample width {width}")
+    y = y.reshape(-1, n_ch).mean(axis=1)
+    if rate != sr:
+        g = np.gcd(int(rate), int(sr))
+        y = resample_poly(y, sr // g, rate // g).astype(np.float32)
+    return y.astype(np.float32)
+
+
+class Music2MIDI(nn.Module):
+    def __init__(self, config_path: str, precision: Optional[str] = None):
+        super().__init__()
+        self.config = load_config(config_path)
+        self.model = T5Transformer(config_path, precision=precision)
+        self.hparams = {"config_path": config_path}
+        self.eval()
+
+    # ------------------------------------------------------------------ Lightning-compatible bits
+    @property
+    def device(self) -> torch.device:
+        return self.model.transformer.device
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, config_path: Optional[str] = None, **kwargs):
+        """Reads a Lightning ``.ckpt`` of the reference (keys ``model.`` + T5Transformer's state dict;
+        ``hyper_parameters.config_path`` used when ``config_path`` is not given)."""
+        ckpt = torch.load(str(checkpoint_path), map_location=map_location or "cpu", weights_only=False)
+        if config_path is None:
+            config_path = (ckpt.get("hyper_parameters") or {}).get("config_path")
+        if config_path is None:
+            raise ValueError("config_path is required (not stored in the checkpoint)")
+        obj = cls(config_path, **kwargs)
+        sd = ckpt.get("state_dict", ckpt)
+        missing, unexpected = obj.load_state_dict(sd, strict=False)
+        # tied aliases may be absent in checkpoints written by other transformers versions
+        tied = {"model.transformer.encoder.embed_tokens.weight", "model.transformer.decoder.embed_tokens.weight"}
+        missing = [k for k in missing if k not in tied]
+        if missing or unexpected:
+            raise RuntimeError(f"checkpoint mismatch: missing={missing} unexpected={list(unexpected)}")
+        return obj
+
+    # ------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def evaluate_batch(self, inputs: ModelInputs):
+        """Generation + decoding half of the reference's evaluate_batch (model.py:55-62); the melody
+        chroma metric itself (music2midi/evaluation.py, mir_eval) is outside this package."""
+        max_num_notes = max(len(notes) for notes in inputs.notes_batch)
+        generated = self.model.generate(inputs, max_length=max_num_notes * 4)
+        decoded = self.model.tokenizer.decode(generated, mode="batched")
+        label_midi = [numpy_to_midi(n) for n in inputs.notes_batch]
+        output_midi = [numpy_to_midi(n) for n in decoded]
+        return None, output_midi, label_midi
+
+    def generate(self, audio_path: Optional[Union[str, Path]] = None, audio_y: Optional[np.ndarray] = None,
+                 sr: Optional[int] = None, cond_index: Optional[List[int]] = None):
+        """Specify either audio_path or audio_y as input.  Returns a PrettyMIDI(-compatible) object."""
+        if audio_path is None and audio_y is None:
+            raise ValueError("Either audio_path or audio_y should be specified")
+        if sr is None:
+            sr = self.config.model.sample_rate
+        else:
+            assert sr == self.config.model.sample_rate
+        if audio_y is None:
+            audio_y = load_audio(audio_path, sr)
+        split_size = int(sr * self.config.dataset.segment_duration)
+        pad = int(np.ceil(len(audio_y) / split_size)) * split_size - len(audio_y)
+        audio_y = np.pad(np.asarray(audio_y), (0, pad), "constant")
+        waveform = torch.from_numpy(audio_y).to(self.device)
+        notes = self.sample_tokens(waveform, split_size, split_duration=self.config.dataset.segment_duration,
+                                   cond_index=cond_index)
+        return numpy_to_midi(notes)
+
+    @torch.no_grad()
+    def generate_tokens(self, waveform: torch.Tensor, split_size: int, cond_index: Optional[List[int]] = None,
+                        max_length: int = 1024) -> List[torch.Tensor]:
+        """Token rows (one per segment, on the device) for a padded 1-D waveform."""
+        n_embeds = len(self.model.conditioning.embeds)
+        tail = waveform.numel() % split_size
+        if tail:  # direct callers with an unpadded waveform: zero-pad the last segment (pad_sequence, model.py:119)
+            waveform = torch.nn.functional.pad(waveform, (0, split_size - tail))
+        segments = waveform.reshape(-1, split_size)
+        inf = self.config.get("inference", {}) or {}
+        chunk = int(inf.get("device_batch_size", inf.get("batch_size", 128)))
+        rows: List[torch.Tensor] = []
+        for i in range(0, segments.shape[0], chunk):
+            wav = segments[i:i + chunk].to(self.device)
+            cond = torch.zeros((wav.shape[0], n_embeds))
+            if cond_index is not None:
+                cond = cond + torch.Tensor(cond_index)
+            cond = cond.long().to(self.device)
+            tokens = self.model.generate(ModelInputs(input_waveform=wav, cond_index=cond), max_length=max_length)
+            rows += [*tokens]
+        return rows
+
+    @torch.no_grad()
+    def sample_tokens(self, waveform: torch.Tensor, split_size: int, split_duration: float,
+                      cond_index: Optional[List[int]] = None) -> np.ndarray:
+        """(N,4) float64 notes [onset_s, offset_s, pitch, velocity] of the whole recording."""
+        rows = self.generate_tokens(waveform, split_size, cond_index, max_length=1024)
+        return self.model.tokenizer.decode(rows, mode="sequential", duration_per_batch=split_duration)

@@ -1,0 +1,315 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via music2midi_b200.engine) against
+(a) golden fixtures recorded from the live reference (tests/golden/make_golden.py) and
+(b) the CPU oracle (oracle/port.py) on the same seeded inputs.
+
+Tolerances (stated once, used below):
+  MEL_TOL_NOISE   max|d| / max|ref| <= 1e-4 on the log-mel (north-star bar; norm per SURVEY.md §0.6)
+  MEL_TOL_TONES   <= 1e-3 in the same norm on the high-dynamic-range tone signal: the reference's own
+                  fp32 FFT is 1.7e-4 away from an fp64 evaluation there, so 1e-4 is not attainable by
+                  any fp32 implementation; the per-case reference-vs-fp64 deviation is in mel.npz.
+  ENC_TOL         max|d| / max|ref| <= 2e-4 for the fp32 encoder output
+  LOGIT_TOL_FP32  max|d| <= 2e-3 absolute on logits (scale ~ +-8) in fp32 mode
+  LOGIT_TOL_BF16  max|d| <= 0.25 absolute and mean|d| <= 0.04 in bf16 mode (bf16 operands, fp32 accumulate)
+  tokens          bit-exact in fp32 mode on rows whose golden top-2 logit gap is >= 2e-3 along the whole
+                  path; on the remaining rows the first divergence must sit at a golden gap < 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from music2midi_b200 import synthetic as syn
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL_NOISE = 1e-4
+MEL_TOL_TONES = 1e-3
+ENC_TOL = 2e-4
+LOGIT_TOL_FP32 = 2e-3
+LOGIT_TOL_BF16_MAX = 0.25
+LOGIT_TOL_BF16_MEAN = 0.04
+STRICT_GAP = 2e-3
+TIE_GAP = 1e-3
+
+DEV = "cuda:0"
+
+
+def candidate_inputs():
+    wave = torch.cat([syn.audio_noise(8, 0), syn.audio_tones(8, 0)])
+    cond = torch.stack([torch.arange(16) % 6, torch.arange(16) % 3], 1)
+    return wave, cond
+
+
+def norm_err(a, ref):
+    a = a.detach().double().cpu()
+    ref = torch.as_tensor(ref).double()
+    return float((a - ref).abs().max() / ref.abs().max())
+
+
+@pytest.fixture(scope="module")
+def cpu_embeds(oracle_weights):
+    """Encoder input embeddings computed by the CPU oracle (isolates the transformer from mel error)."""
+    wave, cond = candidate_inputs()
+    W = oracle_weights
+    return port.conditioning(port.logmel(wave, W.window, W.fb), cond, W.cond_embeds)
+
+
+# ------------------------------------------------------------------------------ log-mel
+@pytest.mark.parametrize("case,tol", [("noise", MEL_TOL_NOISE), ("tones", MEL_TOL_TONES), ("long", MEL_TOL_NOISE),
+                                      ("short", MEL_TOL_TONES)])
+def test_logmel_matches_reference(engine_fp32, report, case, tol):
+    g = golden("mel.npz")
+    wave = {"noise": lambda: syn.audio_noise(2, 11), "tones": lambda: syn.audio_tones(2, 11),
+            "long": lambda: syn.audio_noise(1, 12, samples=66150),
+            "short": lambda: syn.audio_tones(1, 13, samples=5000)}[case]()
+    assert abs(float(wave.double().abs().sum()) - float(g[f"{case}_insum"])) < 1e-6 * float(g[f"{case}_insum"])
+    out = engine_fp32.logmel(wave.to(DEV))
+    ref = torch.from_numpy(g[f"{case}_mel"])
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    err = norm_err(out, ref)
+    f64 = port.logmel(wave, syn.hann_window(), syn.mel_filterbank(), dtype=torch.float64)
+    report(test="logmel", case=case, norm_err_vs_ref=err, abs_err_vs_ref=float((out.cpu() - ref).abs().max()),
+           abs_err_vs_f64=float((out.cpu().double() - f64).abs().max()),
+           ref_abs_err_vs_f64=float(g[f"{case}_ref_vs_f64_maxabs"]), tol=tol)
+    assert err <= tol
+
+
+def test_logmel_silence_is_floor(engine_fp32):
+    out = engine_fp32.logmel(syn.audio_zeros(3).to(DEV))
+    ref = torch.from_numpy(golden("mel.npz")["zeros_mel"])
+    assert out.shape == (3, 188, 384)
+    assert torch.allclose(out.cpu()[:1], ref, rtol=0, atol=2e-6)
+    assert float(out.max() - out.min()) == 0.0
+
+
+def test_logmel_leading_dims_and_empty(engine_fp32):
+    w = syn.audio_noise(6, 5).to(DEV)
+    a = engine_fp32.logmel(w)
+    b = engine_fp32.logmel(w.reshape(2, 3, -1))
+    assert b.shape == (2, 3, 188, 384) and torch.equal(a, b.reshape(6, 188, 384))
+    assert engine_fp32.logmel(w[:0]).shape == (0, 188, 384)
+
+
+def test_logmel_bf16_engine_is_same_fp32_frontend(engine_fp32, engine_bf16):
+    w = syn.audio_noise(2, 6).to(DEV)
+    assert torch.equal(engine_fp32.logmel(w), engine_bf16.logmel(w))
+
+
+# ------------------------------------------------------------------------------ conditioning
+def test_conditioning_exact(engine_fp32, oracle_weights):
+    feat = torch.randn(5, 7, 384, generator=torch.Generator().manual_seed(3))
+    cond = torch.tensor([[0, 0], [5, 2], [3, 1], [1, 1], [2, 0]])
+    out = engine_fp32.condition(feat.to(DEV), cond.to(DEV))
+    assert torch.equal(out.cpu(), port.conditioning(feat, cond, oracle_weights.cond_embeds))
+
+
+def test_conditioning_index_error(engine_fp32):
+    from music2midi_b200.engine import M2MError
+
+    feat = torch.zeros(1, 4, 384, device=DEV)
+    with pytest.raises(M2MError):
+        engine_fp32.condition(feat, torch.tensor([[6, 0]], device=DEV))
+
+
+# ------------------------------------------------------------------------------ encoder
+def test_encoder_matches_reference(engine_fp32, cpu_embeds, report):
+    g = golden("generate.npz")
+    rows = g["enc_rows"].tolist()
+    out = engine_fp32.encode(cpu_embeds[rows].to(DEV))
+    err = norm_err(out, g["enc"])
+    report(test="encoder_fp32", norm_err=err, abs_err=float((out.cpu() - torch.from_numpy(g["enc"])).abs().max()))
+    assert err <= ENC_TOL
+
+
+def test_encoder_matches_oracle_other_lengths(engine_fp32, oracle_weights, report):
+    gen = torch.Generator().manual_seed(5)
+    for L in (1, 7, 190, 261):
+        x = torch.randn(2, L, 384, generator=gen) * 3.0
+        out = engine_fp32.encode(x.to(DEV))
+        ref = port.encoder(x, oracle_weights)
+        err = norm_err(out, ref)
+        report(test="encoder_fp32_oracle", L=L, norm_err=err)
+        assert err <= ENC_TOL
+
+
+def test_encoder_bf16(engine_bf16, cpu_embeds, report):
+    g = golden("generate.npz")
+    out = engine_bf16.encode(cpu_embeds[g["enc_rows"].tolist()].to(DEV))
+    err = norm_err(out, g["enc"])
+    report(test="encoder_bf16", norm_err=err)
+    assert err <= 5e-2
+
+
+# ------------------------------------------------------------------------------ decode: logits
+def _forced_logits(engine, embeds, tokens):
+    toks, logits = engine.generate_from_embeds(embeds.to(DEV), tokens.shape[1], forced=tokens.to(DEV),
+                                               return_logits=True)
+    assert torch.equal(toks.cpu(), tokens)
+    return logits.cpu()
+
+
+def test_decode_logits_fp32(engine_fp32, cpu_embeds, report):
+    g = golden("generate.npz")
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    steps = g["logit_steps"].tolist()
+    logits = _forced_logits(engine_fp32, cpu_embeds, tokens)
+    d = (logits[:, steps] - torch.from_numpy(g["logits"])).abs()
+    report(test="decode_logits_fp32", max_abs=float(d.max()), mean_abs=float(d.mean()),
+           per_step_max=[float(x) for x in d.amax(dim=(0, 2))])
+    assert float(d.max()) <= LOGIT_TOL_FP32
+
+
+def test_decode_logits_bf16(engine_bf16, cpu_embeds, report):
+    g = golden("generate.npz")
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    steps = g["logit_steps"].tolist()
+    logits = _forced_logits(engine_bf16, cpu_embeds, tokens)
+    d = (logits[:, steps] - torch.from_numpy(g["logits"])).abs()
+    agree = float((logits[:, steps].argmax(-1) == torch.from_numpy(g["logits"]).argmax(-1)).float().mean())
+    report(test="decode_logits_bf16", max_abs=float(d.max()), mean_abs=float(d.mean()), argmax_agreement=agree)
+    assert float(d.max()) <= LOGIT_TOL_BF16_MAX and float(d.mean()) <= LOGIT_TOL_BF16_MEAN
+
+
+# ------------------------------------------------------------------------------ decode: greedy tokens
+def _check_tokens(out, tokens, gap, report, label):
+    strict_rows = [r for r in range(tokens.shape[0]) if float(gap[r].min()) >= STRICT_GAP]
+    assert len(strict_rows) >= 4
+    res = []
+    for r in range(tokens.shape[0]):
+        same = torch.equal(out[r], tokens[r])
+        first = None if same else int((out[r] != tokens[r]).nonzero()[0])
+        gap_at = None if same else float(gap[r, first - 1])
+        res.append(dict(row=r, exact=same, first_divergence=first, golden_gap_there=gap_at,
+                        min_gap=float(gap[r].min()), strict=r in strict_rows))
+    report(test=label, rows=res)
+    for e in res:
+        if e["strict"]:
+            assert e["exact"], f"row {e['row']} diverges at {e['first_divergence']} (gap {e['golden_gap_there']})"
+        elif not e["exact"]:
+            assert e["golden_gap_there"] < TIE_GAP, e
+
+
+def test_greedy_tokens_fp32_from_reference_embeds(engine_fp32, cpu_embeds, report):
+    g = golden("generate.npz")
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    out = engine_fp32.generate_from_embeds(cpu_embeds.to(DEV), 1024).cpu()
+    assert out.shape == tokens.shape and out.dtype == torch.int64
+    _check_tokens(out, tokens, torch.from_numpy(g["gap"]), report, "greedy_tokens_fp32_embeds")
+
+
+def test_greedy_tokens_fp32_end_to_end(engine_fp32, report):
+    """waveform -> tokens entirely on the GPU (T5Transformer.generate, transformer.py:41-45)."""
+    g = golden("generate.npz")
+    wave, cond = candidate_inputs()
+    assert abs(float(wave.double().abs().sum()) - float(g["insum"])) < 1e-6 * float(g["insum"])
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    out = engine_fp32.generate(wave.to(DEV), cond.to(DEV), 1024).cpu()
+    assert out.shape == tokens.shape
+    _check_tokens(out, tokens, torch.from_numpy(g["gap"]), report, "greedy_tokens_fp32_e2e")
+
+
+def test_graph_and_plain_launch_agree(engine_fp32, cpu_embeds):
+    e = cpu_embeds[:5].to(DEV)
+    engine_fp32.set_flags(graph=True)
+    a = engine_fp32.generate_from_embeds(e, 200)
+    engine_fp32.set_flags(graph=False)
+    b = engine_fp32.generate_from_embeds(e, 200)
+    engine_fp32.set_flags(graph=True)
+    assert torch.equal(a, b)
+
+
+def test_eos_pad_and_dynamic_length(state_dict, cpu_embeds, report):
+    """Rows finish at different steps: pad after EOS, stop when all rows are done, length cap."""
+    from music2midi_b200.engine import Engine
+
+    g = golden("generate_eos.npz")
+    sd = dict(state_dict)
+    lm = sd["transformer.lm_head.weight"].clone()
+    lm[2] *= float(g["eos_row_scale"])
+    sd["transformer.lm_head.weight"] = lm
+    eng = Engine(torch.device(DEV), "fp32")
+    eng.load_state_dict(sd)
+    rows = g["rows"].tolist()
+    t_all = eng.generate_from_embeds(cpu_embeds[:8].to(DEV), 1024).cpu()
+    t_sub = eng.generate_from_embeds(cpu_embeds[rows].to(DEV), 1024).cpu()
+    t_cap = eng.generate_from_embeds(cpu_embeds[:8].to(DEV), 40).cpu()
+    exp_all = torch.from_numpy(g["tokens_all"].astype(np.int64))
+    exp_sub = torch.from_numpy(g["tokens_subset"].astype(np.int64))
+    exp_cap = torch.from_numpy(g["tokens_cap40"].astype(np.int64))
+    report(test="eos", shapes=[list(t_all.shape), list(t_sub.shape), list(t_cap.shape)],
+           expected=[list(exp_all.shape), list(exp_sub.shape), list(exp_cap.shape)])
+    assert t_sub.shape == exp_sub.shape, "dynamic output length differs from HF"
+    assert torch.equal(t_sub, exp_sub)
+    assert torch.equal(t_cap, exp_cap)
+    # rows that hit EOS early are bit-exact incl. padding; never-finishing rows may hit a near-tie late
+    fin = (exp_all == 2).any(dim=1)
+    assert torch.equal(t_all[fin], exp_all[fin])
+    # skipping finished rows in attention must not change anything
+    eng.set_flags(skip_finished=False)
+    assert torch.equal(eng.generate_from_embeds(cpu_embeds[rows].to(DEV), 1024).cpu(), exp_sub)
+    eng.close()
+
+
+def test_generate_edge_cases(engine_fp32, cpu_embeds):
+    e = cpu_embeds[:3].to(DEV)
+    assert engine_fp32.generate_from_embeds(e, 1).cpu().tolist() == [[1], [1], [1]]
+    two = engine_fp32.generate_from_embeds(e, 2).cpu()
+    assert two.shape == (3, 2) and two[:, 0].tolist() == [1, 1, 1]
+    assert engine_fp32.generate_from_embeds(e[:0], 16).shape[0] == 0
+    from music2midi_b200.engine import M2MError
+
+    with pytest.raises(M2MError):
+        engine_fp32.generate_from_embeds(e, 1025)
+
+
+def test_bf16_greedy_is_self_consistent(engine_bf16, cpu_embeds, report):
+    """bf16 throughput mode: graph vs plain launches agree; tokens agree with fp32 golden while the
+    golden gap is large compared with bf16 logit error."""
+    g = golden("generate.npz")
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    out = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 1024).cpu()
+    match = [int((out[r] != tokens[r]).nonzero()[0]) if not torch.equal(out[r], tokens[r]) else 1024
+             for r in range(16)]
+    report(test="greedy_tokens_bf16", first_divergence=match)
+    engine_bf16.set_flags(graph=False)
+    out2 = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 1024).cpu()
+    engine_bf16.set_flags(graph=True)
+    assert torch.equal(out, out2)
+    assert out[:, 0].eq(1).all() and out.shape == (16, 1024)
+
+
+# ------------------------------------------------------------------------------ teacher-forced forward
+def test_decoder_forward_matches_reference(engine_fp32, oracle_weights, report):
+    g = golden("forward.npz")
+    tk = golden("tokenizer.npz")
+    wave = syn.audio_noise(3, 21)
+    cond = torch.from_numpy(g["cond"])
+    notes = tuple(tk[f"notes_{i}"] for i in g["notes_idx"].tolist())
+    labels = port.tokenize(notes)
+    labels_m = labels.masked_fill(labels == 0, -100)
+    dec_in = torch.cat([torch.ones(labels.shape[0], 1, dtype=torch.long), labels_m[:, :-1]], 1)
+    dec_in = dec_in.masked_fill(dec_in == -100, 0)
+    mel = engine_fp32.logmel(wave.to(DEV))
+    enc = engine_fp32.encode(engine_fp32.condition(mel, cond.to(DEV)))
+    logits = engine_fp32.decoder_forward(enc, dec_in.to(DEV)).cpu()
+    ref = torch.from_numpy(g["logits"])
+    assert logits.shape == ref.shape
+    d = (logits - ref).abs()
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, 400), labels_m.reshape(-1), ignore_index=-100)
+    report(test="decoder_forward_fp32", max_abs=float(d.max()), loss=float(loss), ref_loss=float(g["loss"]))
+    assert float(d.max()) <= LOGIT_TOL_FP32
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4
+
+
+# ------------------------------------------------------------------------------ host-buffer API
+def test_transcribe_host_matches_device_api(engine_fp32):
+    wave, cond = candidate_inputs()
+    wave, cond = wave[:5], cond[:5]
+    dev = engine_fp32.generate(wave.to(DEV), cond.to(DEV), 64).cpu().numpy()
+    toks, lens = engine_fp32.transcribe_host(wave.numpy(), cond.numpy(), 64, device_batch=2)
+    assert toks.shape == (5, 64) and np.array_equal(toks[:, : dev.shape[1]], dev)
+    assert lens.tolist() == [64] * 5
+    toks0, _ = engine_fp32.transcribe_host(wave.numpy(), None, 64, device_batch=8)
+    dev0 = engine_fp32.generate(wave.to(DEV), torch.zeros_like(cond).to(DEV), 64).cpu().numpy()
+    assert np.array_equal(toks0, dev0)
