@@ -157,8 +157,15 @@ typedef struct m2m_stats {
 int m2m_stats_reset(m2m_ctx* ctx);
 int m2m_stats_get(m2m_ctx* ctx, m2m_stats* out);
 /* flags: bit0 = use CUDA graph for the decode step (default 1), bit1 = time attention kernels with
- * events (forces non-graph launches), bit2 = skip finished rows in attention (default 1). */
+ * events (forces non-graph launches), bit2 = skip finished rows in attention (default 1),
+ * bit3 = route bf16 GEMMs to the CUDA-core kernel instead of tcgen05 (A/B testing). */
 int m2m_set_flags(m2m_ctx* ctx, uint32_t flags);
+
+/* Test hook (tests/test_gpu_gemm.py): d_C fp32 [M,N] = A[M,K] . W[N,K]^T with bf16 device operands, through
+ * path 0 = CUDA-core kernel, 1 = tcgen05 kernel (automatic tile), 2 / 3 = tcgen05 with BN = 64 / 128.
+ * Synchronises the stream, so a faulting kernel is reported by this call. */
+int m2m_debug_gemm_bf16(m2m_ctx* ctx, const void* d_A, const void* d_W, int M, int N, int K, float* d_C, int path,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,7 @@ SYMBOLS = {
     "m2m_stats_reset": (C.c_int, [_P]),
     "m2m_stats_get": (C.c_int, [_P, C.POINTER(Stats)]),
     "m2m_set_flags": (C.c_int, [_P, C.c_uint32]),
+    "m2m_debug_gemm_bf16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -8,10 +8,12 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 namespace m2m {
@@ -137,7 +139,19 @@ template <typename T, typename Epi>
 static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K, Epi epi, const DecState* st,
                 cudaStream_t s) {
   if (M == 0) return 0;
-  cudaError_t e = launch_gemm_simt(RowMajorA<T>{A, lda}, W, K, M, N, K, epi, st, s, c->num_sms);
+  cudaError_t e;
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (!(c->flags & 8u) && tc::supported(M, N, K, lda)) {
+      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms);
+      if (e != cudaSuccess) {
+        set_error("tcgen05 gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
+        return M2M_ERR_CUDA;
+      }
+      c->stats.kernel_launches++;
+      return 0;
+    }
+  }
+  e = launch_gemm_simt(RowMajorA<T>{A, lda}, W, K, M, N, K, epi, st, s, c->num_sms);
   if (e != cudaSuccess) {
     set_error("gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
     return M2M_ERR_CUDA;
@@ -1070,6 +1084,35 @@ int m2m_transcribe_host(m2m_ctx* c, const float* h_wave, int64_t n_seg, int S, c
         if (r[j] == c->cfg.eos_id) { n = j + 1; break; }
       h_lens[i] = n;
     }
+  return 0;
+}
+
+int m2m_debug_gemm_bf16(m2m_ctx* c, const void* d_A, const void* d_W, int M, int N, int K, float* d_C, int path,
+                        void* stream) {
+  if (!c) { set_error("null ctx"); return M2M_ERR_INVALID; }
+  M2M_TRY(ensure_device(c));
+  cudaStream_t s = (cudaStream_t)stream;
+  M2M_REQUIRE(M >= 0 && N > 0 && N % 4 == 0 && K > 0 && K % 16 == 0, "debug gemm: unsupported shape %dx%dx%d", M, N, K);
+  const bf16* A = (const bf16*)d_A;
+  const bf16* W = (const bf16*)d_W;
+  cudaError_t e;
+  if (path == 1) {
+    M2M_REQUIRE(tc::supported(M, N, K, K), "debug gemm: shape not supported by the tcgen05 kernel");
+    e = tc::launch(A, K, W, M, N, K, EpiStore<float>{d_C, N}, nullptr, s, c->num_sms);
+  } else if (path == 2) {
+    M2M_REQUIRE(tc::supported(M, N, K, K), "debug gemm: shape not supported by the tcgen05 kernel");
+    e = tc::launch_cfg<64, 4>(A, K, W, M, N, K, EpiStore<float>{d_C, N}, nullptr, s);
+  } else if (path == 3) {
+    M2M_REQUIRE(tc::supported(M, N, K, K), "debug gemm: shape not supported by the tcgen05 kernel");
+    e = tc::launch_cfg<128, 3>(A, K, W, M, N, K, EpiStore<float>{d_C, N}, nullptr, s);
+  } else {
+    e = launch_gemm_simt(RowMajorA<bf16>{A, K}, W, K, M, N, K, EpiStore<float>{d_C, N}, nullptr, s, c->num_sms);
+  }
+  if (e != cudaSuccess) {
+    set_error("debug gemm launch failed: %s", cudaGetErrorString(e));
+    return M2M_ERR_CUDA;
+  }
+  M2M_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

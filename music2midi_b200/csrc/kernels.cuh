@@ -160,100 +160,153 @@ __global__ void __launch_bounds__(256) seq_attn_kernel(const T* __restrict__ Q, 
 }
 
 // ------------------------------------------------------------------ KV-cached decode attention (a8)
-// One warp per (row b, head h); a block is 4 warps = 4 heads of one row; grid = (H/4, B).
-// Cache layout [b][j][h][64] (key stride `key_stride` elements, batch stride `row_stride`): every key of a (b, h) pair is one 128 B (bf16) / 256 B (fp32) line,
-// read with 16-byte loads (LPK lanes per key), perfectly coalesced.  Online softmax per key slot,
-// slots merged with shuffles at the end: K and V are each read exactly once.
+// HBM-bound streaming kernel.  One block (4 warps) per (row b, head h); caches are head-major
+// [b][h][j][64], so the K and the V of a (b, h) pair are two contiguous streams.  Thread 0 drives a
+// STAGES-deep ring of 4 KB + 4 KB shared-memory buffers with 1-D bulk async copies (TMA engine,
+// cp.async.bulk + mbarrier complete_tx): bytes in flight do not cost registers, ~9 blocks/SM keep
+// ~200 KB per SM outstanding.  The 4 warps split every chunk (8 lanes per key, 16-byte conflict-free
+// LDS), each keeps an online-softmax state (fp32), merged by shuffles and once through shared memory:
+// K and V are read from HBM exactly once.
 //   SELF:  nkeys = st->t + 1 (the current token's K/V were written by the QKV GEMM epilogue),
 //          score += bias[h][t - j]   (decoder unidirectional bucket LUT, block 0's table)
 //   CROSS: nkeys fixed (encoder length), no bias.
 template <typename T, bool SELF, bool FAST_EXP>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ q, const T* __restrict__ Kc,
-                                                          const T* __restrict__ Vc, size_t row_stride, int key_stride,
-                                                          int nkeys_fixed,
+                                                          const T* __restrict__ Vc, size_t row_stride,
+                                                          size_t head_stride, int nkeys_fixed,
                                                           const float* __restrict__ bias, int bias_ld,
                                                           T* __restrict__ out, int H,
                                                           const DecState* __restrict__ st,
                                                           const uint8_t* __restrict__ finished) {
   if (st->done) return;
-  const int b = blockIdx.y;
+  const int h = blockIdx.x, b = blockIdx.y;
   if (finished != nullptr && finished[b]) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x * 4 + warp;
-  const int inner = H * 64;
-  constexpr int VEC = Vec16<T>::N;     // elements per 16 B
-  constexpr int LPK = 64 / VEC;        // lanes per key
-  constexpr int KPI = 32 / LPK;        // keys per warp-wide load
-  constexpr int U = 4;                 // unroll: U*KPI keys in flight per warp
+  constexpr int STAGES = 3;
+  constexpr int CHUNK_BYTES = 4096;                    // per K and per V
+  constexpr int CH = CHUNK_BYTES / (64 * (int)sizeof(T));  // keys per chunk: 32 (bf16) / 16 (fp32)
+  constexpr int VEC = Vec16<T>::N;                     // elements per 16 B
+  constexpr int LPK = 64 / VEC;                        // lanes per key
+  constexpr int KPI = 32 / LPK;                        // keys per warp-wide shared-memory load
+  constexpr int SLICE = CH / 4;                        // keys of a chunk handled by one warp
+  constexpr int ITERS = SLICE / KPI;
+  __shared__ __align__(128) uint8_t ring[STAGES][2][CHUNK_BYTES];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ float part_acc[4][64];
+  __shared__ float part_m[4], part_l[4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane / LPK, c = lane % LPK;
+  const int inner = H * 64;
   const int t = st->t;
   const int nkeys = SELF ? t + 1 : nkeys_fixed;
+  const int nchunks = (nkeys + CH - 1) / CH;
+  const uint8_t* kg = reinterpret_cast<const uint8_t*>(Kc + (size_t)b * row_stride + (size_t)h * head_stride);
+  const uint8_t* vg = reinterpret_cast<const uint8_t*>(Vc + (size_t)b * row_stride + (size_t)h * head_stride);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 4);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int i) {  // thread 0 only: start the copies of chunk i
+    const int s = i % STAGES, u = i / STAGES;
+    if (u > 0) mbar_wait(&empty_bar[s], (u - 1) & 1);
+    const int nk = min(CH, nkeys - i * CH);
+    const uint32_t bytes = (uint32_t)nk * 64u * (uint32_t)sizeof(T);
+    mbar_expect_tx(&full_bar[s], 2 * bytes);
+    bulk_g2s(ring[s][0], kg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s]);
+    bulk_g2s(ring[s][1], vg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < STAGES - 1 && i < nchunks; ++i) issue(i);
 
   float qv[VEC];
   Vec16<T>::load(q + (size_t)b * inner + h * 64 + c * VEC, qv);
-  const T* kb = Kc + (size_t)b * row_stride + h * 64 + c * VEC;
-  const T* vb = Vc + (size_t)b * row_stride + h * 64 + c * VEC;
   const float* bh = SELF ? bias + (size_t)h * bias_ld : nullptr;
-
   float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
 
-  for (int j0 = 0; j0 < nkeys; j0 += KPI * U) {
-    float kv[U][VEC], vv[U][VEC];
+  for (int i = 0; i < nchunks; ++i) {
+    if (tid == 0 && i + STAGES - 1 < nchunks) issue(i + STAGES - 1);
+    const int s = i % STAGES;
+    mbar_wait(&full_bar[s], (i / STAGES) & 1);
+    const T* ks = reinterpret_cast<const T*>(ring[s][0]);
+    const T* vs = reinterpret_cast<const T*>(ring[s][1]);
+    float kv[ITERS][VEC], vv[ITERS][VEC];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int j = j0 + u * KPI + g;
-      if (j < nkeys) {
-        Vec16<T>::load(kb + (size_t)j * key_stride, kv[u]);
-        Vec16<T>::load(vb + (size_t)j * key_stride, vv[u]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) kv[u][e] = vv[u][e] = 0.f;
-      }
+    for (int it = 0; it < ITERS; ++it) {
+      const int kl = warp * SLICE + it * KPI + g;
+      Vec16<T>::load_shared(ks + kl * 64 + c * VEC, kv[it]);
+      Vec16<T>::load_shared(vs + kl * 64 + c * VEC, vv[it]);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int j = j0 + u * KPI + g;
-      float s = 0.f;
+    for (int it = 0; it < ITERS; ++it) {
+      const int j = i * CH + warp * SLICE + it * KPI + g;
+      float sc = 0.f;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) s = fmaf(qv[e], kv[u][e], s);
+      for (int e = 0; e < VEC; ++e) sc = fmaf(qv[e], kv[it][e], sc);
 #pragma unroll
-      for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (j < nkeys) {
-        if (SELF) s += __ldg(bh + (t - j));
-        float mn = fmaxf(m, s);
-        float sc = FAST_EXP ? __expf(m - mn) : expf(m - mn);  // m = -inf -> 0
-        float p = FAST_EXP ? __expf(s - mn) : expf(s - mn);
-        l = l * sc + p;
+      for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      if (j < nkeys) {  // lanes of invalid keys read stale shared memory: ignored
+        if (SELF) sc += __ldg(bh + (t - j));
+        const float mn = fmaxf(m, sc);
+        const float r = FAST_EXP ? __expf(m - mn) : expf(m - mn);  // m = -inf -> 0
+        const float pw = FAST_EXP ? __expf(sc - mn) : expf(sc - mn);
+        l = l * r + pw;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * sc + p * vv[u][e];
+        for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * r + pw * vv[it][e];
         m = mn;
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
-  // merge the KPI key slots
+  // merge the KPI key slots of this warp
 #pragma unroll
   for (int o = LPK; o < 32; o <<= 1) {
-    float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-    float l2 = __shfl_xor_sync(0xffffffffu, l, o);
-    float mn = fmaxf(m, m2);
-    float s1 = (m == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m - mn) : expf(m - mn));
-    float s2 = (m2 == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m2 - mn) : expf(m2 - mn));
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, m2);
+    const float s1 = (m == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m - mn) : expf(m - mn));
+    const float s2 = (m2 == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m2 - mn) : expf(m2 - mn));
     l = l * s1 + l2 * s2;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      float a2 = __shfl_xor_sync(0xffffffffu, acc[e], o);
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], o);
       acc[e] = acc[e] * s1 + a2 * s2;
     }
     m = mn;
   }
   if (g == 0) {
-    float inv = 1.f / l;
-    float o[VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) o[e] = acc[e] * inv;
-    Vec16<T>::store(out + (size_t)b * inner + h * 64 + c * VEC, o);
+    for (int e = 0; e < VEC; ++e) part_acc[warp][c * VEC + e] = acc[e];
+    if (c == 0) {
+      part_m[warp] = m;
+      part_l[warp] = l;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {  // merge the 4 warps; lane owns dims 2*lane, 2*lane+1
+    float mm = fmaxf(fmaxf(part_m[0], part_m[1]), fmaxf(part_m[2], part_m[3]));
+    float ll = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float pm = part_m[w];
+      const float sw = (pm == -INFINITY) ? 0.f : (FAST_EXP ? __expf(pm - mm) : expf(pm - mm));
+      ll += part_l[w] * sw;
+      o0 += part_acc[w][2 * lane] * sw;
+      o1 += part_acc[w][2 * lane + 1] * sw;
+    }
+    const float inv = 1.f / ll;
+    T* op = out + (size_t)b * inner + h * 64 + 2 * lane;
+    op[0] = from_f<T>(o0 * inv);
+    op[1] = from_f<T>(o1 * inv);
   }
 }
 

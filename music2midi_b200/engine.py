@@ -200,9 +200,21 @@ class Engine:
                 tokens.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p)))
         return tokens, lens
 
+    def debug_gemm_bf16(self, A: torch.Tensor, W: torch.Tensor, path: int) -> torch.Tensor:
+        """Test hook: fp32 C = A @ W.T for bf16 CUDA operands through one GEMM kernel (see the header)."""
+        A = self._in(A, torch.bfloat16, "A")
+        W = self._in(W, torch.bfloat16, "W")
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            check(self.lib.m2m_debug_gemm_bf16(self._ctx, _ptr(A), _ptr(W), M, N, K, _ptr(out), path, self._stream()))
+        return out
+
     # ------------------------------------------------------------------ introspection
-    def set_flags(self, graph: bool = True, time_attention: bool = False, skip_finished: bool = True):
-        f = (1 if graph else 0) | (2 if time_attention else 0) | (4 if skip_finished else 0)
+    def set_flags(self, graph: bool = True, time_attention: bool = False, skip_finished: bool = True,
+                  no_tensor_cores: bool = False):
+        f = (1 if graph else 0) | (2 if time_attention else 0) | (4 if skip_finished else 0) | (8 if no_tensor_cores else 0)
         check(self.lib.m2m_set_flags(self._ctx, f))
 
     def stats(self, reset: bool = False) -> Dict[str, float]:
