@@ -171,19 +171,14 @@ static int rmsnorm(m2m_ctx* c, const float* x, const float* w, TO* y, size_t row
 }
 
 template <typename T, bool CAUSAL>
-static int seq_attn(m2m_ctx* c, const T* Q, int ldq, const T* K, const T* V, int ldkv, T* O, int ldo, int B, int Lq,
-                    int Lk, const float* bias, int bias_ld, int bias_zero, cudaStream_t s) {
-  size_t smem = ((size_t)Lk * (65 + 64) + 8 * (size_t)Lk) * sizeof(float);
-  if (smem > 227 * 1024) {
-    set_error("sequence attention: key length %d needs %zu B of shared memory (max 227 KB)", Lk, smem);
-    return M2M_ERR_INVALID;
-  }
+static int seq_attn(m2m_ctx* c, const T* Q, int ldq, const T* K, const T* V, size_t kv_bs, int kv_hs, int kv_js, T* O,
+                    int ldo, int B, int Lq, int Lk, const float* bias, int bias_ld, int bias_zero, cudaStream_t s) {
+  const int KT = Lk <= 256 ? Lk : 128;  // key tile staged in shared memory (single tile for the encoder)
+  size_t smem = ((size_t)KT * (65 + 64) + 8 * (size_t)KT) * sizeof(float);
   auto kern = seq_attn_kernel<T, CAUSAL>;
-  M2M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int q_tile = Lq <= 96 ? Lq : 64;
-  if (q_tile < 8) q_tile = 8;
-  dim3 grid((Lq + q_tile - 1) / q_tile, c->cfg.n_heads, B);
-  kern<<<grid, 256, smem, s>>>(Q, ldq, K, V, ldkv, O, ldo, Lq, Lk, bias, bias_ld, bias_zero, q_tile);
+  M2M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (65 + 64 + 8) * 4));
+  dim3 grid((Lq + SEQ_ATTN_QT - 1) / SEQ_ATTN_QT, c->cfg.n_heads, B);
+  kern<<<grid, 256, smem, s>>>(Q, ldq, K, V, kv_bs, kv_hs, kv_js, O, ldo, Lq, Lk, bias, bias_ld, bias_zero, KT);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -259,8 +254,8 @@ static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d
     const EncLayerW& w = c->enc[l];
     M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
-    M2M_TRY((seq_attn<T, false>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, 3 * I, ao, I, B, L, L, c->enc_bias, c->enc_bias_ld,
-                                g.max_enc_len - 1, s)));
+    M2M_TRY((seq_attn<T, false>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)L * 3 * I, 64, 3 * I, ao, I, B, L, L,
+                                c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s)));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));
@@ -282,8 +277,9 @@ static int cross_kv_impl(m2m_ctx* c, const T* enc_out, int B, int L, cudaStream_
   const size_t M = (size_t)B * L;
   M2M_TRY(c->ckv.ensure((size_t)g.n_layers * M * 2 * I * sizeof(T), &c->generation));
   for (int l = 0; l < g.n_layers; ++l) {
-    T* dst = c->ckv.as<T>() + (size_t)l * M * 2 * I;
-    M2M_TRY(gemm<T>(c, enc_out, D, (const T*)c->dec[l].wckv, (int)M, 2 * I, D, EpiStore<T>{dst, 2 * I}, nullptr, s));
+    T* dst = c->ckv.as<T>() + (size_t)l * M * 2 * I;  // [K block: B*L*I | V block: B*L*I], each [b][h][j][64]
+    M2M_TRY(gemm<T>(c, enc_out, D, (const T*)c->dec[l].wckv, (int)M, 2 * I, D,
+                    EpiHeadMajorKV<T>{dst, dst + M * I, I, L}, nullptr, s));
   }
   return 0;
 }
@@ -312,24 +308,25 @@ static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const in
   const size_t self_layer = (size_t)B * Tmax * I;  // elements per K (or V) per layer
   const size_t cross_layer = (size_t)B * L * 2 * I;
   constexpr bool FAST = !std::is_same<T, float>::value;
-  dim3 agrid(g.n_heads / 4, B);
+  dim3 agrid(g.n_heads, B);
   for (int l = 0; l < g.n_layers; ++l) {
     const DecLayerW& w = c->dec[l];
     T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer;
     T* vc = kc + self_layer;
     const T* ck = c->ckv.as<T>() + (size_t)l * cross_layer;
     M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, B, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, B, 3 * I, D, EpiQKVCache<T>{q, kc, vc, I, (size_t)Tmax * I}, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, B, 3 * I, D,
+                    EpiQKVCache<T>{q, kc, vc, I, (size_t)Tmax * 64, (size_t)Tmax * I}, st, s));
     if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
-    decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, I, 0, c->dec_bias,
-                                                            g.max_positions, ao, g.n_heads, st, fin_skip);
+    decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
+                                                            c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
     LAUNCH_CHECK(c);
     if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, B, D, I, EpiResidual{x, D}, st, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, B, st, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, B, I, D, EpiStore<T>{q, I}, st, s));
-    decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, ck + I, (size_t)L * 2 * I, 2 * I, L, nullptr, 0, ao,
-                                                             g.n_heads, st, fin_skip);
+    decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, ck + (size_t)B * L * I, (size_t)L * I, (size_t)L * 64, L,
+                                                             nullptr, 0, ao, g.n_heads, st, fin_skip);
     LAUNCH_CHECK(c);
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, B, D, I, EpiResidual{x, D}, st, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, B, st, s));
@@ -572,12 +569,12 @@ static int decoder_forward_impl(m2m_ctx* c, const float* d_enc, int B, int L, co
     const T* ck = c->ckv.as<T>() + (size_t)l * Me * 2 * I;
     M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
-    M2M_TRY((seq_attn<T, true>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, 3 * I, ao, I, B, Ld, Ld, c->dec_bias_seq,
-                               2 * g.max_positions - 1, g.max_positions - 1, s)));
+    M2M_TRY((seq_attn<T, true>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)Ld * 3 * I, 64, 3 * I, ao, I, B, Ld, Ld,
+                               c->dec_bias_seq, 2 * g.max_positions - 1, g.max_positions - 1, s)));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, (int)M, I, D, EpiStore<T>{q, I}, nullptr, s));
-    M2M_TRY((seq_attn<T, false>(c, q, I, ck, ck + I, 2 * I, ao, I, B, Ld, L, nullptr, 0, 0, s)));
+    M2M_TRY((seq_attn<T, false>(c, q, I, ck, ck + Me * I, (size_t)L * I, L * 64, 64, ao, I, B, Ld, L, nullptr, 0, 0, s)));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));

@@ -75,19 +75,36 @@ struct EpiGatedGelu {
     p[1] = from_f<TC>(gelu_new(v[2]) * v[3]);
   }
 };
-// Decode-step fused QKV: cols [0,I) -> q[m, :], [I,2I) -> K cache row (m, t), [2I,3I) -> V cache.
+// Decode-step fused QKV: cols [0,I) -> q[m, :], [I,2I) -> K cache, [2I,3I) -> V cache at position t of the
+// head-major self-attention cache [b][h][t][64].
 template <typename TC>
 struct EpiQKVCache {
   TC* q;
   TC* kc;
   TC* vc;
-  int inner;          // I = 512
-  size_t row_stride;  // elements per batch row in the cache = Tmax * I
+  int inner;           // I = H * 64
+  size_t head_stride;  // Tmax * 64
+  size_t row_stride;   // H * Tmax * 64
   __device__ __forceinline__ void operator()(int m, int n, const float v[4], const DecState* st) const {
     int seg = n / inner, c = n - seg * inner;
     TC* dst = seg == 0 ? q + (size_t)m * inner + c
-                       : (seg == 1 ? kc : vc) + (size_t)m * row_stride + (size_t)st->t * inner + c;
+                       : (seg == 1 ? kc : vc) + (size_t)m * row_stride + (size_t)(c >> 6) * head_stride +
+                             (size_t)st->t * 64 + (c & 63);
     store4(dst, v);
+  }
+};
+// Cross-attention K/V for all encoder positions: rows m = (b, j), cols [0,I) -> K, [I,2I) -> V, written
+// head-major [b][h][j][64] so that decode attention streams each (b, h) contiguously.
+template <typename TC>
+struct EpiHeadMajorKV {
+  TC* k;
+  TC* v;
+  int inner, L;
+  __device__ __forceinline__ void operator()(int m, int n, const float val[4], const DecState*) const {
+    int seg = n / inner, c = n - seg * inner;
+    int b = m / L, j = m - b * L;
+    TC* dst = (seg == 0 ? k : v) + ((size_t)b * (inner >> 6) + (c >> 6)) * ((size_t)L * 64) + (size_t)j * 64 + (c & 63);
+    store4(dst, val);
   }
 };
 // DFT power: W rows interleaved (2f = cos_f, 2f+1 = sin_f):  P[m, f] = re^2 + im^2

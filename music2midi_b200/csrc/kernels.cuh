@@ -87,75 +87,103 @@ __global__ void embed_kernel(const int64_t* __restrict__ tok, const float* __res
 }
 
 // ------------------------------------------------------------------ full-sequence attention (a7, a10)
-// One block per (query tile, head, batch).  qkv rows are (b, l) with columns [q | k | v] or separate
-// pointers with their own leading dimensions.  scores = q.k + bias[h][(j - i) + bias_zero] (+ causal
-// mask), fp32 softmax, out = P V.  K/V of the (b, h) pair are staged in shared memory as fp32.
-// No 1/sqrt(d) scaling (T5).  d_kv == 64.
+// One block (8 warps) per (tile of 64 queries, head, batch).  Element (b, h, j, d) of K/V lives at
+// b*kv_bs + h*kv_hs + j*kv_js + d.  scores = q.k + bias[h][(j - i) + bias_zero] (+ causal mask), fp32
+// online softmax over key tiles of KT keys staged in shared memory as fp32, out = P V / l.
+// No 1/sqrt(d) scaling (T5).  d_kv == 64.  The encoder (L = 190) is a single key tile.
+constexpr int SEQ_ATTN_QT = 64;   // queries per block
+constexpr int SEQ_ATTN_QPW = 8;   // queries per warp
 template <typename T, bool CAUSAL>
 __global__ void __launch_bounds__(256) seq_attn_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K,
-                                                       const T* __restrict__ V, int ldkv, T* __restrict__ O, int ldo,
-                                                       int Lq, int Lk, const float* __restrict__ bias, int bias_ld,
-                                                       int bias_zero, int q_tile) {
+                                                       const T* __restrict__ V, size_t kv_bs, int kv_hs, int kv_js,
+                                                       T* __restrict__ O, int ldo, int Lq, int Lk,
+                                                       const float* __restrict__ bias, int bias_ld, int bias_zero,
+                                                       int KT) {
   extern __shared__ __align__(16) float smem[];
   const int h = blockIdx.y, b = blockIdx.z;
-  const int q0 = blockIdx.x * q_tile;
-  const int q1 = min(Lq, q0 + q_tile);
+  const int q0 = blockIdx.x * SEQ_ATTN_QT;
+  const int q1 = min(Lq, q0 + SEQ_ATTN_QT);
   const int nk = CAUSAL ? min(Lk, q1) : Lk;  // keys needed by this query tile
-  float* Ks = smem;                  // [nk][65]
-  float* Vs = Ks + (size_t)Lk * 65;  // [nk][64]
-  float* Ps = Vs + (size_t)Lk * 64;  // [8 warps][Lk]
+  float* Ks = smem;                  // [KT][65]
+  float* Vs = Ks + (size_t)KT * 65;  // [KT][64]
+  float* Ps = Vs + (size_t)KT * 64;  // [8 warps][KT]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* P = Ps + (size_t)warp * KT;
 
-  for (int i = tid; i < nk * 16; i += 256) {
-    int j = i >> 4, c = (i & 15) * 4;
-    float kv[4], vv[4];
-    load4(K + ((size_t)b * Lk + j) * ldkv + h * 64 + c, kv);
-    load4(V + ((size_t)b * Lk + j) * ldkv + h * 64 + c, vv);
+  float m_[SEQ_ATTN_QPW], l_[SEQ_ATTN_QPW], o0_[SEQ_ATTN_QPW], o1_[SEQ_ATTN_QPW];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      Ks[j * 65 + c + e] = kv[e];
-      Vs[j * 64 + c + e] = vv[e];
+  for (int qi = 0; qi < SEQ_ATTN_QPW; ++qi) {
+    m_[qi] = -INFINITY;
+    l_[qi] = o0_[qi] = o1_[qi] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < nk; k0 += KT) {
+    const int kn = min(KT, nk - k0);
+    __syncthreads();  // previous tile fully consumed
+    for (int i = tid; i < kn * 16; i += 256) {
+      int j = i >> 4, c = (i & 15) * 4;
+      float kv[4], vv[4];
+      load4(K + (size_t)b * kv_bs + (size_t)h * kv_hs + (size_t)(k0 + j) * kv_js + c, kv);
+      load4(V + (size_t)b * kv_bs + (size_t)h * kv_hs + (size_t)(k0 + j) * kv_js + c, vv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        Ks[j * 65 + c + e] = kv[e];
+        Vs[j * 64 + c + e] = vv[e];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qi = 0; qi < SEQ_ATTN_QPW; ++qi) {
+      const int i = q0 + warp + 8 * qi;
+      if (i >= q1) continue;  // warp-uniform
+      const int lim = CAUSAL ? min(kn, i + 1 - k0) : kn;  // keys of this tile visible to query i
+      if (lim <= 0) continue;
+      float q[64];
+      const T* qp = Q + ((size_t)b * Lq + i) * ldq + h * 64;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) load4(qp + c, q + c);
+      float mx = -INFINITY;
+      for (int j = lane; j < lim; j += 32) {
+        const float* kr = Ks + j * 65;
+        float sc = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) sc = fmaf(q[d], kr[d], sc);
+        if (bias != nullptr) sc += bias[(size_t)h * bias_ld + (k0 + j - i) + bias_zero];
+        P[j] = sc;
+        mx = fmaxf(mx, sc);
+      }
+      mx = warp_max(mx);
+      const float mn = fmaxf(m_[qi], mx);
+      const float r = expf(m_[qi] - mn);  // first tile: exp(-inf) = 0
+      float sum = 0.f;
+      for (int j = lane; j < lim; j += 32) {
+        float p = expf(P[j] - mn);
+        P[j] = p;
+        sum += p;
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      float o0 = o0_[qi] * r, o1 = o1_[qi] * r;
+      for (int j = 0; j < lim; ++j) {
+        const float p = P[j];
+        o0 = fmaf(p, Vs[j * 64 + lane], o0);
+        o1 = fmaf(p, Vs[j * 64 + lane + 32], o1);
+      }
+      o0_[qi] = o0;
+      o1_[qi] = o1;
+      l_[qi] = l_[qi] * r + sum;
+      m_[qi] = mn;
+      __syncwarp();  // P is reused by the next query of this warp
     }
   }
-  __syncthreads();
-
-  float* P = Ps + (size_t)warp * Lk;
-  for (int i = q0 + warp; i < q1; i += 8) {
-    float q[64];
-    const T* qp = Q + ((size_t)b * Lq + i) * ldq + h * 64;
 #pragma unroll
-    for (int c = 0; c < 64; c += 4) load4(qp + c, q + c);
-    const int lim = CAUSAL ? i + 1 : nk;
-    float mx = -INFINITY;
-    for (int j = lane; j < lim; j += 32) {
-      const float* kr = Ks + j * 65;
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < 64; ++d) s = fmaf(q[d], kr[d], s);
-      if (bias != nullptr) s += bias[(size_t)h * bias_ld + (j - i) + bias_zero];
-      P[j] = s;
-      mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < lim; j += 32) {
-      float p = expf(P[j] - mx);
-      P[j] = p;
-      sum += p;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    float inv = 1.f / sum;
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < lim; ++j) {
-      float p = P[j] * inv;  // HF normalises the weights before the PV product
-      o0 = fmaf(p, Vs[j * 64 + lane], o0);
-      o1 = fmaf(p, Vs[j * 64 + lane + 32], o1);
-    }
+  for (int qi = 0; qi < SEQ_ATTN_QPW; ++qi) {
+    const int i = q0 + warp + 8 * qi;
+    if (i >= q1) continue;
+    const float inv = 1.f / l_[qi];
     T* op = O + ((size_t)b * Lq + i) * ldo + h * 64;
-    op[lane] = from_f<T>(o0);
-    op[lane + 32] = from_f<T>(o1);
-    __syncwarp();
+    op[lane] = from_f<T>(o0_[qi] * inv);
+    op[lane + 32] = from_f<T>(o1_[qi] * inv);
   }
 }
 
