@@ -268,8 +268,8 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
+            try:  # one ncu --set full capture of this kernel; DRAM bytes scale with the algorithmic bytes
+                traffic = json.load(open(tp))["traffic_over_algorithmic"] * st["attn_bytes"] / n_launch
             except Exception:
                 traffic = None
         roofline = {

@@ -97,11 +97,12 @@ struct m2m_ctx {
   float *window = nullptr, *dft_basis = nullptr, *band_w = nullptr, *cond_emb = nullptr;
   int *band_start = nullptr, *band_len = nullptr, *cond_off = nullptr, *cond_rows = nullptr;
   int n_freq = 0, dft_rows = 0, max_band = 32, enc_bias_ld = 0;
-  void* dft_basis_tc = nullptr;  // bf16 split basis for the tcgen05 path (optional)
+  bf16* dft_basis3 = nullptr;  // [3][basis_split_rows][n_fft] bf16: hi/mid/lo terms of the DFT basis (tcgen05 path)
+  int basis_split_rows = 0;
 
   // workspaces
   int64_t generation = 0;
-  DevBuf mel_power, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
+  DevBuf mel_power, mel_a3, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
   DevBuf ckv, skv;  // cross / self KV caches, all layers
   DevBuf dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err;
   DevBuf tf_x, tf_h, tf_qkv, tf_ao, tf_g, tf_q;  // teacher-forced decoder
@@ -184,21 +185,45 @@ static int seq_attn(m2m_ctx* c, const T* Q, int ldq, const T* K, const T* V, siz
 }
 
 // ------------------------------------------------------------------ log-mel
+// Two data paths for the DFT (both followed by the banded mel + clamp + log kernel):
+//   tcgen05: frame_split_kernel (frames x window -> 3 bf16 terms, L2-resident slab) -> gemm_tc_kernel<NSPLIT=3>
+//            (six bf16 products into one fp32 TMEM accumulator, EpiPower epilogue)
+//   fp32   : gemm_simt_kernel<FrameA, EpiPower> (frames built on the fly, FFMA)
+static bool mel_use_tc(const m2m_ctx* c) {
+  if (c->flags & 16u) return false;
+  if (c->flags & 32u) return true;
+  return c->cfg.precision == M2M_BF16;
+}
+
 static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_mel, cudaStream_t s) {
   const m2m_config& g = c->cfg;
   M2M_REQUIRE(B >= 0 && S > g.n_fft / 2, "logmel: need S > n_fft/2 = %d for reflect padding (got S=%d)", g.n_fft / 2, S);
   if (B == 0) return 0;
   const int T = 1 + S / g.hop;
   const size_t M = (size_t)B * T;
+  M2M_REQUIRE(M < (1u << 30), "logmel: too many frames (%zu)", M);
   const int ldp = (int)align_up(c->n_freq, 4);
-  // frames are processed in slabs so that the power spectrum stays L2-resident between the two kernels
-  const size_t slab_rows = 16384;  // 16384 x 1028 x 4 B = 67 MB < 126 MB L2
+  const bool use_tc = mel_use_tc(c) && g.n_fft % tc::BK == 0;
+  // frames are processed in slabs so that the intermediates stay L2-resident between the kernels
+  const size_t slab_rows = use_tc ? 4096 : 16384;  // tc: 3 x 4096 x 2048 bf16 = 50 MB (+17 MB power) < 126 MB L2
   M2M_TRY(c->mel_power.ensure(std::min(M, slab_rows) * ldp * sizeof(float), &c->generation));
+  if (use_tc) M2M_TRY(c->mel_a3.ensure(3 * slab_rows * g.n_fft * sizeof(bf16), &c->generation));
   for (size_t r0 = 0; r0 < M; r0 += slab_rows) {
     size_t rows = std::min(slab_rows, M - r0);
-    FrameA a{d_wave, c->window, S, T, g.hop, g.n_fft / 2, (int)r0};
-    cudaError_t e = launch_gemm_simt(a, c->dft_basis, g.n_fft, (int)rows, c->dft_rows, g.n_fft,
-                                     EpiPower{c->mel_power.as<float>(), ldp, c->n_freq}, nullptr, s, c->num_sms);
+    EpiPower epi{c->mel_power.as<float>(), ldp, c->n_freq};
+    cudaError_t e;
+    if (use_tc) {
+      size_t total = rows * (size_t)(g.n_fft / 8);
+      unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16);
+      frame_split_kernel<<<blocks, 256, 0, s>>>(d_wave, c->window, c->mel_a3.as<bf16>(), S, T, g.hop, g.n_fft, (int)r0,
+                                                (int)rows, slab_rows * g.n_fft);
+      LAUNCH_CHECK(c);
+      e = tc::launch_cfg<128, 2, EpiPower, 3>(c->mel_a3.as<bf16>(), g.n_fft, c->dft_basis3, (int)rows, c->dft_rows,
+                                              g.n_fft, epi, nullptr, s, (int)slab_rows, c->basis_split_rows);
+    } else {
+      FrameA a{d_wave, c->window, S, T, g.hop, g.n_fft / 2, (int)r0};
+      e = launch_gemm_simt(a, c->dft_basis, g.n_fft, (int)rows, c->dft_rows, g.n_fft, epi, nullptr, s, c->num_sms);
+    }
     if (e != cudaSuccess) {
       set_error("logmel DFT launch failed: %s", cudaGetErrorString(e));
       return M2M_ERR_CUDA;
@@ -752,7 +777,7 @@ int m2m_ctx_destroy(m2m_ctx* c) {
   cudaDeviceSynchronize();
   if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
-  DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
+  DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
                     &c->enc_out, &c->ckv, &c->skv, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
                     &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->tf_x, &c->tf_h,
                     &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave, &c->host_cond, &c->host_tokens};
@@ -918,6 +943,38 @@ int m2m_finalize_weights(m2m_ctx* c) {
   size_t o_basis = ab.push_f32(basis);
   basis.clear();
   basis.shrink_to_fit();
+  // the same basis as three bf16 terms (hi + mid + lo of the fp64 value), each term padded to a multiple of the
+  // 128-row tile, stacked [3][basis_split_rows][n_fft] for the tcgen05 path
+  const int basis_split_rows = (int)align_up((size_t)dft_rows, 128);
+  size_t o_basis3 = 0;
+  {
+    std::vector<uint16_t> b3((size_t)3 * basis_split_rows * g.n_fft, 0);
+    std::vector<double> ct(g.n_fft), stb(g.n_fft);
+    for (int r = 0; r < g.n_fft; ++r) {
+      double ang = 2.0 * M_PI * (double)r / (double)g.n_fft;
+      ct[r] = cos(ang);
+      stb[r] = sin(ang);
+    }
+    auto bf2d = [](uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return (double)f; };
+    const size_t term = (size_t)basis_split_rows * g.n_fft;
+    for (int row = 0; row < 2 * n_freq; ++row) {
+      const int f = row >> 1;
+      for (int k = 0; k < g.n_fft; ++k) {
+        int r = (int)(((long long)f * k) % g.n_fft);
+        double x = (row & 1) ? stb[r] : ct[r];
+        uint16_t hi = f2bf((float)x);
+        double r1 = x - bf2d(hi);
+        uint16_t mid = f2bf((float)r1);
+        double r2 = r1 - bf2d(mid);
+        uint16_t lo = f2bf((float)r2);
+        size_t idx = (size_t)row * g.n_fft + k;
+        b3[idx] = hi;
+        b3[term + idx] = mid;
+        b3[2 * term + idx] = lo;
+      }
+    }
+    o_basis3 = ab.push_bytes(b3.data(), b3.size() * 2);
+  }
 
   // banded mel filterbank
   M2M_TRY(get_staged(c, "spectrogram.melspectrogram.mel_scale.fb", (size_t)n_freq * D, &t));
@@ -980,6 +1037,8 @@ int m2m_finalize_weights(m2m_ctx* c) {
   c->dec_bias = F32(o_decb);
   c->dec_bias_seq = F32(o_decbs);
   c->dft_basis = F32(o_basis);
+  c->dft_basis3 = reinterpret_cast<bf16*>(base + o_basis3);
+  c->basis_split_rows = basis_split_rows;
   c->dft_rows = dft_rows;
   c->n_freq = n_freq;
   c->band_start = reinterpret_cast<int*>(base + o_bs);

@@ -68,20 +68,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+// NSPLIT = 1: plain bf16 operands.  NSPLIT = 3: each fp32 operand is carried as three bf16 terms
+// (x = hi + mid + lo, 24 mantissa bits) stacked along the row dimension of its tensor map; the kernel issues
+// the six products whose magnitude is >= 2^-16 of the leading one (hi.hi, hi.mid, mid.hi, hi.lo, mid.mid,
+// lo.hi) into the same fp32 TMEM accumulator: fp32-class accuracy on the bf16 tensor pipe (used by the DFT).
+template <int BN, int STAGES, int NSPLIT = 1>
 struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int A_BYTES = BM * BK * 2;  // per split term
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */;
 };
 
-template <int BN, int STAGES, typename Epi>
+template <int BN, int STAGES, int NSPLIT, typename Epi>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
-                                                      Epi epi, const DecState* __restrict__ st) {
+                                                      int a_split_rows, int w_split_rows, Epi epi,
+                                                      const DecState* __restrict__ st) {
   if (st != nullptr && st->done) return;
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -122,8 +127,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         mbar_wait(&empty_bar[s], ph ^ 1);  // first pass over the ring returns immediately
         mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
         uint8_t* a_dst = smem + s * L::STAGE_BYTES;
-        tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-        tma_load_2d(a_dst + L::A_BYTES, &tmW, &full_bar[s], kb * BK, n0);
+        uint8_t* w_dst = a_dst + NSPLIT * L::A_BYTES;
+#pragma unroll
+        for (int sp = 0; sp < NSPLIT; ++sp) {
+          tma_load_2d(a_dst + sp * L::A_BYTES, &tmA, &full_bar[s], kb * BK, sp * a_split_rows + m0);
+          tma_load_2d(w_dst + sp * L::B_BYTES, &tmW, &full_bar[s], kb * BK, sp * w_split_rows + n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -135,12 +144,21 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(a_addr);
-        const uint64_t bdesc = make_smem_desc(a_addr + L::A_BYTES);
+        const uint32_t w_addr = a_addr + NSPLIT * L::A_BYTES;
+        bool first = kb == 0;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
-          umma(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        for (int sa = 0; sa < NSPLIT; ++sa) {
+#pragma unroll
+          for (int sb = 0; sb < NSPLIT - sa; ++sb) {
+            const uint64_t adesc = make_smem_desc(a_addr + sa * L::A_BYTES);
+            const uint64_t bdesc = make_smem_desc(w_addr + sb * L::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
+              umma(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+              first = false;
+            }
+          }
         }
         umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
       }
@@ -212,15 +230,17 @@ inline bool supported(int M, int N, int K, int lda) {
   return M >= 1 && K % BK == 0 && N % 4 == 0 && lda % 8 == 0;
 }
 
-template <int BN, int STAGES, typename Epi>
+// NSPLIT = 3: A is [3 * a_split_rows, K] and W is [3 * w_split_rows, K] (terms stacked along rows).
+template <int BN, int STAGES, typename Epi, int NSPLIT = 1>
 inline cudaError_t launch_cfg(const bf16* A, int lda, const bf16* W, int M, int N, int K, Epi epi, const DecState* st,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int a_split_rows = 0, int w_split_rows = 0) {
   CUtensorMap ta, tw;
-  if (!make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM) ||
-      !make_map(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN))
+  const uint64_t a_rows = NSPLIT == 1 ? (uint64_t)M : (uint64_t)NSPLIT * a_split_rows;
+  const uint64_t w_rows = NSPLIT == 1 ? (uint64_t)N : (uint64_t)NSPLIT * w_split_rows;
+  if (!make_map(&ta, A, a_rows, (uint64_t)K, (uint64_t)lda, BM) || !make_map(&tw, W, w_rows, (uint64_t)K, (uint64_t)K, BN))
     return cudaErrorInvalidValue;
-  auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
-  constexpr int smem = SmemLayout<BN, STAGES>::TOTAL;
+  auto kern = gemm_tc_kernel<BN, STAGES, NSPLIT, Epi>;
+  constexpr int smem = SmemLayout<BN, STAGES, NSPLIT>::TOTAL;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -228,7 +248,7 @@ inline cudaError_t launch_cfg(const bf16* A, int lda, const bf16* W, int M, int 
     attr_set = true;
   }
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  kern<<<grid, 192, smem, stream>>>(ta, tw, M, N, K, epi, st);
+  kern<<<grid, 192, smem, stream>>>(ta, tw, M, N, K, a_split_rows, w_split_rows, epi, st);
   return cudaGetLastError();
 }
 

@@ -410,6 +410,56 @@ __global__ void step_advance_kernel(DecState* st, int greedy_stop) {
   st->unfinished = 0;
 }
 
+// ------------------------------------------------------------------ framing + window + 3-way bf16 split (a3)
+// A3[s][m][n] for s = hi, mid, lo: frame m = (b, t), sample n:  x = wave[b][reflect(t*hop + n - n_fft/2)] * w[n],
+// hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid).  Pure streaming kernel: 16-byte loads of the
+// window, 8 outputs per thread per term written as one 16-byte store; the waveform (reused by n_fft/hop = 8
+// overlapping frames) comes from L1/L2.  `rows` frames starting at global frame `m_off`.
+__global__ void __launch_bounds__(256) frame_split_kernel(const float* __restrict__ wave, const float* __restrict__ window,
+                                                          bf16* __restrict__ A3, int S, int T, int hop, int n_fft,
+                                                          int m_off, int rows, size_t split_stride) {
+  const int chunks = n_fft / 8;
+  const size_t total = (size_t)rows * chunks;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / chunks), ch = (int)(i - (size_t)r * chunks);
+    const int m = m_off + r;
+    const int b = m / T, t = m - b * T;
+    const float* w = wave + (size_t)b * S;
+    const int n0 = ch * 8;
+    const int base = t * hop + n0 - n_fft / 2;
+    float x[8], wv[8];
+    load4(window + n0, wv);
+    load4(window + n0 + 4, wv + 4);
+    if (base >= 0 && base + 7 < S && (reinterpret_cast<uintptr_t>(w + base) & 15) == 0) {
+      load4(w + base, x);
+      load4(w + base + 4, x + 4);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int j = base + e;
+        j = j < 0 ? -j : j;
+        j = j >= S ? 2 * (S - 1) - j : j;
+        x[e] = __ldg(w + j);
+      }
+    }
+    float hi[8], mid[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = x[e] * wv[e];
+      const float h = __bfloat162float(__float2bfloat16_rn(v));
+      const float r1 = v - h;
+      const float md = __bfloat162float(__float2bfloat16_rn(r1));
+      hi[e] = h;
+      mid[e] = md;
+      lo[e] = r1 - md;
+    }
+    bf16* dst = A3 + (size_t)r * n_fft + n0;
+    Vec16<bf16>::store(dst, hi);
+    Vec16<bf16>::store(dst + split_stride, mid);
+    Vec16<bf16>::store(dst + 2 * split_stride, lo);
+  }
+}
+
 // ------------------------------------------------------------------ banded mel + clamp + log (a3)
 // out[m, j] = log(max(sum_i P[m, start[j] + i] * w[j][i], 1e-6)); the HTK filterbank is 0.5 % dense
 // (<= 14 taps per filter), so the projection is a banded gather, not a GEMM.

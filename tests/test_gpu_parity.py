@@ -56,20 +56,23 @@ def cpu_embeds(oracle_weights):
 
 
 # ------------------------------------------------------------------------------ log-mel
+@pytest.mark.parametrize("path", ["simt", "tc"])  # fp32 CUDA-core DFT / tcgen05 split-bf16 DFT
 @pytest.mark.parametrize("case,tol", [("noise", MEL_TOL_NOISE), ("tones", MEL_TOL_TONES), ("long", MEL_TOL_NOISE),
                                       ("short", MEL_TOL_TONES)])
-def test_logmel_matches_reference(engine_fp32, report, case, tol):
+def test_logmel_matches_reference(engine_fp32, report, case, tol, path):
     g = golden("mel.npz")
+    engine_fp32.set_flags(mel=path)
     wave = {"noise": lambda: syn.audio_noise(2, 11), "tones": lambda: syn.audio_tones(2, 11),
             "long": lambda: syn.audio_noise(1, 12, samples=66150),
             "short": lambda: syn.audio_tones(1, 13, samples=5000)}[case]()
     assert abs(float(wave.double().abs().sum()) - float(g[f"{case}_insum"])) < 1e-6 * float(g[f"{case}_insum"])
     out = engine_fp32.logmel(wave.to(DEV))
+    engine_fp32.set_flags()
     ref = torch.from_numpy(g[f"{case}_mel"])
     assert out.shape == ref.shape and out.dtype == torch.float32
     err = norm_err(out, ref)
     f64 = port.logmel(wave, syn.hann_window(), syn.mel_filterbank(), dtype=torch.float64)
-    report(test="logmel", case=case, norm_err_vs_ref=err, abs_err_vs_ref=float((out.cpu() - ref).abs().max()),
+    report(test="logmel", case=case, path=path, norm_err_vs_ref=err, abs_err_vs_ref=float((out.cpu() - ref).abs().max()),
            abs_err_vs_f64=float((out.cpu().double() - f64).abs().max()),
            ref_abs_err_vs_f64=float(g[f"{case}_ref_vs_f64_maxabs"]), tol=tol)
     assert err <= tol
@@ -91,9 +94,16 @@ def test_logmel_leading_dims_and_empty(engine_fp32):
     assert engine_fp32.logmel(w[:0]).shape == (0, 188, 384)
 
 
-def test_logmel_bf16_engine_is_same_fp32_frontend(engine_fp32, engine_bf16):
-    w = syn.audio_noise(2, 6).to(DEV)
-    assert torch.equal(engine_fp32.logmel(w), engine_bf16.logmel(w))
+def test_logmel_frontend_is_fp32_class_in_both_engines(engine_fp32, engine_bf16):
+    """The bf16 engine keeps an fp32-accurate frontend (split-bf16 DFT on tcgen05): same tolerance."""
+    w = syn.audio_noise(2, 6)
+    ref = port.logmel(w, syn.hann_window(), syn.mel_filterbank())
+    for eng in (engine_fp32, engine_bf16):
+        assert norm_err(eng.logmel(w.to(DEV)), ref) <= MEL_TOL_NOISE
+    engine_bf16.set_flags(mel="simt")
+    a = engine_bf16.logmel(w.to(DEV))
+    engine_bf16.set_flags()
+    assert torch.equal(a, engine_fp32.logmel(w.to(DEV)))
 
 
 # ------------------------------------------------------------------------------ conditioning
@@ -207,6 +217,17 @@ def test_greedy_tokens_fp32_end_to_end(engine_fp32, report):
     out = engine_fp32.generate(wave.to(DEV), cond.to(DEV), 1024).cpu()
     assert out.shape == tokens.shape
     _check_tokens(out, tokens, torch.from_numpy(g["gap"]), report, "greedy_tokens_fp32_e2e")
+
+
+def test_greedy_tokens_fp32_with_tensor_core_frontend(engine_fp32, report):
+    """fp32 transformer behind the tcgen05 split-bf16 DFT frontend: tokens still match the reference."""
+    g = golden("generate.npz")
+    wave, cond = candidate_inputs()
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    engine_fp32.set_flags(mel="tc")
+    out = engine_fp32.generate(wave.to(DEV), cond.to(DEV), 1024).cpu()
+    engine_fp32.set_flags()
+    _check_tokens(out, tokens, torch.from_numpy(g["gap"]), report, "greedy_tokens_fp32_tc_frontend")
 
 
 def test_graph_and_plain_launch_agree(engine_fp32, cpu_embeds):
