@@ -165,27 +165,35 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       umma_commit(&tmem_full_bar);  // accumulator complete
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32).  tcgen05.ld hands every thread one output row
+    // (32 columns); the 32x32 block is transposed through shared memory (the operand ring is idle by now) so
+    // that 8 adjacent lanes cover 32 consecutive columns of one row: epilogue loads/stores are full sectors.
     const int q = warp & 3;
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
+    float(*tile)[36] = reinterpret_cast<float(*)[36]>(smem + q * (32 * 36 * 4));
+    const int trow = lane >> 3, tcol = (lane & 7) * 4;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= N) break;  // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (m < M) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = n0 + c0 + 4 * j;
-          if (n < N) {
-            float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                          __uint_as_float(r[4 * j + 3])};
-            epi(m, n, v, st);
-          }
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(&tile[lane][4 * j]) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
+      const int n = n0 + c0 + tcol;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + trow;
+        const int m = m0 + q * 32 + row;
+        const float4 t4 = *reinterpret_cast<const float4*>(&tile[row][tcol]);
+        if (m < M && n < N) {
+          float v[4] = {t4.x, t4.y, t4.z, t4.w};
+          epi(m, n, v, st);
         }
       }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
