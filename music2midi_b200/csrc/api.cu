@@ -3,6 +3,7 @@
 // include/m2m_b200.h.  One context per GPU; kernels are launched on the caller's stream.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -14,6 +15,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "attn_tc.cuh"
 #include "kernels.cuh"
 
 namespace m2m {
@@ -67,6 +69,8 @@ struct DecLayerW {
   void *wqkv, *wo, *wcq, *wckv, *wco, *wi, *wffo;
 };
 
+constexpr int MAX_MB = 8;
+
 struct GraphKey {
   int B = -1, L = -1, max_length = -1;
   int64_t generation = -1;
@@ -107,11 +111,14 @@ struct m2m_ctx {
   DevBuf dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err;
   DevBuf tf_x, tf_h, tf_qkv, tf_ao, tf_g, tf_q;  // teacher-forced decoder
   DevBuf host_wave, host_cond, host_tokens;      // m2m_transcribe_host device staging
-  int* h_done = nullptr;                         // pinned
-  cudaEvent_t poll_ev = nullptr;
+  int* h_done = nullptr;                         // pinned, one flag per micro-batch
+  cudaEvent_t poll_ev[MAX_MB] = {};
+  cudaEvent_t join_ev[MAX_MB] = {};
+  cudaStream_t mb_streams[MAX_MB] = {};
   cudaStream_t own_stream = nullptr;
+  int n_microbatch = 1;  // >1: independent decode chains on separate streams (M2M_MICROBATCHES); measured gain ~1 %
 
-  cudaGraphExec_t step_graph = nullptr;
+  std::vector<cudaGraphExec_t> step_graphs;  // one per micro-batch
   GraphKey graph_key;
   size_t graph_nodes = 0;
 
@@ -279,8 +286,22 @@ static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d
     const EncLayerW& w = c->enc[l];
     M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
-    M2M_TRY((seq_attn<T, false>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)L * 3 * I, 64, 3 * I, ao, I, B, L, L,
-                                c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s)));
+    bool attn_done = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (!(c->flags & 64u) && tc::enc_attn_supported(L, I, 3 * I)) {  // fused tcgen05 attention
+        cudaError_t e = tc::launch_enc_attn(qkv, 3 * I, B, L, g.n_heads, ao, I, c->enc_bias, c->enc_bias_ld,
+                                            g.max_enc_len - 1, s);
+        if (e != cudaSuccess) {
+          set_error("tcgen05 encoder attention launch failed: %s", cudaGetErrorString(e));
+          return M2M_ERR_CUDA;
+        }
+        c->stats.kernel_launches++;
+        attn_done = true;
+      }
+    }
+    if (!attn_done)
+      M2M_TRY((seq_attn<T, false>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)L * 3 * I, 64, 3 * I, ao, I, B, L, L,
+                                  c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s)));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));
@@ -315,53 +336,61 @@ struct StepTiming {
   size_t next = 0;
 };
 
+// One decode step for the rows [r0, r0 + nb) of a batch of B rows ("micro-batch"): every per-row buffer is
+// addressed with the row offset, the micro-batch has its own DecState, so several micro-batches run as
+// independent chains on different streams (their latency-bound GEMMs overlap the HBM-bound attention of the
+// others).
 template <typename T>
-static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const int64_t* forced, float* logits_all,
-                              bool skip_finished, StepTiming* tm, cudaStream_t s) {
+static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, int max_length, const int64_t* forced,
+                              float* logits_all, bool skip_finished, StepTiming* tm, cudaStream_t s) {
   const m2m_config& g = c->cfg;
   const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
   const int Tmax = max_length;  // cache positions per row
-  DecState* st = c->dec_state.as<DecState>();
-  float* x = c->dec_x.as<float>();
-  T* h = c->dec_h.as<T>();
-  T* q = c->dec_q.as<T>();
-  T* ao = c->dec_ao.as<T>();
-  T* gg = c->dec_g.as<T>();
-  float* logits = c->dec_logits.as<float>();
-  uint8_t* fin = c->dec_finished.as<uint8_t>();
+  DecState* st = c->dec_state.as<DecState>() + mb;
+  float* x = c->dec_x.as<float>() + (size_t)r0 * D;
+  T* h = c->dec_h.as<T>() + (size_t)r0 * D;
+  T* q = c->dec_q.as<T>() + (size_t)r0 * I;
+  T* ao = c->dec_ao.as<T>() + (size_t)r0 * I;
+  T* gg = c->dec_g.as<T>() + (size_t)r0 * F;
+  float* logits = c->dec_logits.as<float>() + (size_t)r0 * V;
+  uint8_t* fin = c->dec_finished.as<uint8_t>() + r0;
+  int64_t* tokens = c->dec_tokens.as<int64_t>() + (size_t)r0 * max_length;
+  if (forced) forced += (size_t)r0 * max_length;
+  if (logits_all) logits_all += (size_t)r0 * (max_length - 1) * V;
   const uint8_t* fin_skip = skip_finished ? fin : nullptr;
   const size_t self_layer = (size_t)B * Tmax * I;  // elements per K (or V) per layer
   const size_t cross_layer = (size_t)B * L * 2 * I;
   constexpr bool FAST = !std::is_same<T, float>::value;
-  dim3 agrid(g.n_heads, B);
+  dim3 agrid(g.n_heads, nb);
   for (int l = 0; l < g.n_layers; ++l) {
     const DecLayerW& w = c->dec[l];
-    T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer;
+    T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer + (size_t)r0 * Tmax * I;
     T* vc = kc + self_layer;
-    const T* ck = c->ckv.as<T>() + (size_t)l * cross_layer;
-    M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, B, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, B, 3 * I, D,
+    const T* ck = c->ckv.as<T>() + (size_t)l * cross_layer + (size_t)r0 * L * I;
+    const T* cv = ck + (size_t)B * L * I;
+    M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, nb, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, nb, 3 * I, D,
                     EpiQKVCache<T>{q, kc, vc, I, (size_t)Tmax * 64, (size_t)Tmax * I}, st, s));
     if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
     decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
                                                             c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
     LAUNCH_CHECK(c);
     if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
-    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, B, D, I, EpiResidual{x, D}, st, s));
-    M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, B, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, B, I, D, EpiStore<T>{q, I}, st, s));
-    decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, ck + (size_t)B * L * I, (size_t)L * I, (size_t)L * 64, L,
-                                                             nullptr, 0, ao, g.n_heads, st, fin_skip);
+    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, nb, D, I, EpiResidual{x, D}, st, s));
+    M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, nb, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, nb, I, D, EpiStore<T>{q, I}, st, s));
+    decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, cv, (size_t)L * I, (size_t)L * 64, L, nullptr, 0, ao,
+                                                             g.n_heads, st, fin_skip);
     LAUNCH_CHECK(c);
-    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, B, D, I, EpiResidual{x, D}, st, s));
-    M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, B, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, B, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
-    M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, B, D, F, EpiResidual{x, D}, st, s));
+    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, nb, D, I, EpiResidual{x, D}, st, s));
+    M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, nb, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, nb, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
+    M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, nb, D, F, EpiResidual{x, D}, st, s));
   }
-  M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, B, st, s));
-  M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, B, V, D, EpiStore<float>{logits, V}, st, s));
-  select_token_kernel<<<B, 128, 0, s>>>(logits, V, c->dec_tokens.as<int64_t>(), max_length, forced, fin, c->shared, x, D,
-                                        logits_all, st, g.pad_id, g.eos_id);
+  M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, nb, st, s));
+  M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, nb, V, D, EpiStore<float>{logits, V}, st, s));
+  select_token_kernel<<<nb, 128, 0, s>>>(logits, V, tokens, max_length, forced, fin, c->shared, x, D, logits_all, st,
+                                         g.pad_id, g.eos_id);
   LAUNCH_CHECK(c);
   step_advance_kernel<<<1, 1, 0, s>>>(st, forced == nullptr ? 1 : 0);
   LAUNCH_CHECK(c);
@@ -369,17 +398,17 @@ static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const in
 }
 
 __global__ void decode_init_kernel(int64_t* tokens, int ld, uint8_t* finished, float* x, const float* table, int D,
-                                   int B, int bos, DecState* st, int max_length) {
+                                   int B, int bos, DecState* st, int n_states, int max_length) {
   int b = blockIdx.x;
   if (threadIdx.x == 0) {
     tokens[(size_t)b * ld] = bos;
     finished[b] = 0;
-    if (b == 0) {
-      st->t = 0;
-      st->done = max_length <= 1 ? 1 : 0;
-      st->final_len = max_length <= 1 ? 1 : max_length;
-      st->unfinished = 0;
-      st->max_length = max_length;
+    if (b < n_states) {
+      st[b].t = 0;
+      st[b].done = max_length <= 1 ? 1 : 0;
+      st[b].final_len = max_length <= 1 ? 1 : max_length;
+      st[b].unfinished = 0;
+      st[b].max_length = max_length;
     }
   }
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x)
@@ -411,23 +440,27 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   M2M_TRY(c->dec_logits.ensure((size_t)B * V * sizeof(float), &c->generation));
   M2M_TRY(c->dec_finished.ensure((size_t)B, &c->generation));
   M2M_TRY(c->dec_tokens.ensure((size_t)B * max_length * sizeof(int64_t), &c->generation));
-  M2M_TRY(c->dec_state.ensure(sizeof(DecState), &c->generation));
-
-  int64_t* tokens = c->dec_tokens.as<int64_t>();
-  M2M_CUDA(cudaMemsetAsync(tokens, 0, (size_t)B * max_length * sizeof(int64_t), s));  // pad_id == 0 rows
-  if (g.pad_id != 0) {
-    set_error("pad_token_id != 0 is not supported");
-    return M2M_ERR_INVALID;
-  }
-  decode_init_kernel<<<B, 128, 0, s>>>(tokens, max_length, c->dec_finished.as<uint8_t>(), c->dec_x.as<float>(),
-                                       c->shared, D, B, g.bos_id, c->dec_state.as<DecState>(), max_length);
-  LAUNCH_CHECK(c);
+  M2M_TRY(c->dec_state.ensure(MAX_MB * sizeof(DecState), &c->generation));
 
   const int n_steps = max_length - 1;
   const bool timing = (c->flags & 2u) != 0;
   const bool plain = d_forced == nullptr && d_logits == nullptr;
   const bool use_graph = (c->flags & 1u) && plain && !timing;
   const bool skip_finished = (c->flags & 4u) && plain;
+  // micro-batches: independent decode chains on their own streams (only for the plain, graph-replayed path)
+  int nmb = 1;
+  if (use_graph && B >= 2 * 128) nmb = std::min<int>(c->n_microbatch, std::min(MAX_MB, B / 128));
+  if (nmb < 1) nmb = 1;
+  int mb_r0[MAX_MB + 1];
+  for (int i = 0; i <= nmb; ++i) mb_r0[i] = (int)((int64_t)B * i / nmb);
+
+  int64_t* tokens = c->dec_tokens.as<int64_t>();
+  M2M_CUDA(cudaMemsetAsync(tokens, 0, (size_t)B * max_length * sizeof(int64_t), s));  // pad_id == 0 rows
+  decode_init_kernel<<<B, 128, 0, s>>>(tokens, max_length, c->dec_finished.as<uint8_t>(),
+                                                       c->dec_x.as<float>(), c->shared, D, B, g.bos_id,
+                                                       c->dec_state.as<DecState>(), nmb, max_length);
+  LAUNCH_CHECK(c);
+
   StepTiming tm;
   if (timing) {
     size_t need = (size_t)n_steps * g.n_layers * 2;
@@ -440,75 +473,99 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   }
 
   if (use_graph && n_steps > 0) {
-    GraphKey key;
-    key.B = B; key.L = L; key.max_length = max_length; key.generation = c->generation; key.flags = c->flags;
-    bool hit = c->step_graph && c->graph_key.B == B && c->graph_key.L == L && c->graph_key.max_length == max_length &&
+    bool hit = !c->step_graphs.empty() && (int)c->step_graphs.size() == nmb && c->graph_key.B == B &&
+               c->graph_key.L == L && c->graph_key.max_length == max_length &&
                c->graph_key.generation == c->generation && c->graph_key.flags == c->flags;
     if (!hit) {
-      if (c->step_graph) {
-        cudaGraphExecDestroy(c->step_graph);
-        c->step_graph = nullptr;
+      for (auto ge : c->step_graphs) cudaGraphExecDestroy(ge);
+      c->step_graphs.clear();
+      for (int i = 0; i < nmb; ++i) {
+        cudaGraph_t graph = nullptr;
+        int64_t launches_before = c->stats.kernel_launches;
+        // capture on the context's own stream (the caller's may be the legacy default stream, which cannot be
+        // captured); the instantiated graphs are launched on the micro-batch streams.
+        cudaStream_t cs = c->own_stream;
+        M2M_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_step_launch<T>(c, B, mb_r0[i], mb_r0[i + 1] - mb_r0[i], i, L, max_length, nullptr, nullptr,
+                                       skip_finished, nullptr, cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        c->graph_nodes = (size_t)(c->stats.kernel_launches - launches_before);
+        c->stats.kernel_launches = launches_before;
+        if (rc != 0) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        if (ce != cudaSuccess) {
+          set_error("decode-step graph capture failed: %s", cudaGetErrorString(ce));
+          return M2M_ERR_CUDA;
+        }
+        cudaGraphExec_t ge = nullptr;
+        M2M_CUDA(cudaGraphInstantiate(&ge, graph, 0));
+        cudaGraphDestroy(graph);
+        c->step_graphs.push_back(ge);
       }
-      cudaGraph_t graph = nullptr;
-      int64_t launches_before = c->stats.kernel_launches;
-      // capture on the context's own stream (the caller's may be the legacy default stream, which
-      // cannot be captured); the instantiated graph is then launched on the caller's stream.
-      cudaStream_t cs = c->own_stream;
-      M2M_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      int rc = decode_step_launch<T>(c, B, L, max_length, nullptr, nullptr, skip_finished, nullptr, cs);
-      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-      c->graph_nodes = (size_t)(c->stats.kernel_launches - launches_before);
-      c->stats.kernel_launches = launches_before;
-      if (rc != 0) {
-        if (graph) cudaGraphDestroy(graph);
-        return rc;
-      }
-      if (ce != cudaSuccess) {
-        set_error("decode-step graph capture failed: %s", cudaGetErrorString(ce));
-        return M2M_ERR_CUDA;
-      }
-      M2M_CUDA(cudaGraphInstantiate(&c->step_graph, graph, 0));
-      cudaGraphDestroy(graph);
-      c->graph_key = key;
+      c->graph_key.B = B; c->graph_key.L = L; c->graph_key.max_length = max_length;
+      c->graph_key.generation = c->generation; c->graph_key.flags = c->flags;
     }
   }
 
   M2M_CUDA(cudaEventCreate(&ev_begin));
   M2M_CUDA(cudaEventCreate(&ev_end));
   M2M_CUDA(cudaEventRecord(ev_begin, s));
-  *c->h_done = 0;
-  bool poll_pending = false;
-  int steps_launched = 0;
+  // micro-batch i > 0 runs on its own stream, forked from and joined back into the caller's stream
+  cudaStream_t mbs[MAX_MB];
+  for (int i = 0; i < nmb; ++i) mbs[i] = (nmb == 1) ? s : c->mb_streams[i];
+  if (nmb > 1)
+    for (int i = 0; i < nmb; ++i) M2M_CUDA(cudaStreamWaitEvent(mbs[i], ev_begin, 0));
+  bool pending[MAX_MB] = {false}, stopped[MAX_MB] = {false};
+  for (int i = 0; i < nmb; ++i) c->h_done[i] = 0;
   for (int step = 0; step < n_steps; ++step) {
-    if (use_graph) {
-      M2M_CUDA(cudaGraphLaunch(c->step_graph, s));
-      c->stats.kernel_launches += (int64_t)c->graph_nodes;
-    } else {
-      M2M_TRY(decode_step_launch<T>(c, B, L, max_length, d_forced, d_logits, skip_finished, &tm, s));
-    }
-    ++steps_launched;
-    // lagging, non-blocking stop detection: the device sets st->done; later launches are no-ops
-    if (d_forced == nullptr && (step & 15) == 15) {
-      if (poll_pending && cudaEventQuery(c->poll_ev) == cudaSuccess) {
-        poll_pending = false;
-        if (*c->h_done) break;
+    bool all_stopped = true;
+    for (int i = 0; i < nmb; ++i) {
+      if (stopped[i]) continue;
+      all_stopped = false;
+      if (use_graph) {
+        M2M_CUDA(cudaGraphLaunch(c->step_graphs[i], mbs[i]));
+        c->stats.kernel_launches += (int64_t)c->graph_nodes;
+      } else {
+        M2M_TRY(decode_step_launch<T>(c, B, 0, B, 0, L, max_length, d_forced, d_logits, skip_finished, &tm, s));
       }
-      if (!poll_pending) {
-        M2M_CUDA(cudaMemcpyAsync(c->h_done, &c->dec_state.as<DecState>()->done, sizeof(int), cudaMemcpyDeviceToHost, s));
-        M2M_CUDA(cudaEventRecord(c->poll_ev, s));
-        poll_pending = true;
+      // lagging, non-blocking stop detection: the device sets st->done; later launches are no-ops
+      if (d_forced == nullptr && (step & 15) == 15) {
+        if (pending[i] && cudaEventQuery(c->poll_ev[i]) == cudaSuccess) {
+          pending[i] = false;
+          if (c->h_done[i]) stopped[i] = true;
+        }
+        if (!pending[i] && !stopped[i]) {
+          M2M_CUDA(cudaMemcpyAsync(&c->h_done[i], &(c->dec_state.as<DecState>() + i)->done, sizeof(int),
+                                   cudaMemcpyDeviceToHost, mbs[i]));
+          M2M_CUDA(cudaEventRecord(c->poll_ev[i], mbs[i]));
+          pending[i] = true;
+        }
       }
     }
+    if (all_stopped) break;
   }
+  if (nmb > 1)
+    for (int i = 0; i < nmb; ++i) {
+      M2M_CUDA(cudaEventRecord(c->join_ev[i], mbs[i]));
+      M2M_CUDA(cudaStreamWaitEvent(s, c->join_ev[i], 0));
+    }
   M2M_CUDA(cudaEventRecord(ev_end, s));
-  DecState hst;
-  M2M_CUDA(cudaMemcpyAsync(&hst, c->dec_state.p, sizeof(DecState), cudaMemcpyDeviceToHost, s));
+  DecState hsts[MAX_MB];
+  M2M_CUDA(cudaMemcpyAsync(hsts, c->dec_state.p, nmb * sizeof(DecState), cudaMemcpyDeviceToHost, s));
   if (d_tokens)
     M2M_CUDA(cudaMemcpyAsync(d_tokens, tokens, (size_t)B * max_length * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
   M2M_CUDA(cudaStreamSynchronize(s));
-  if (n_steps > 0 && !hst.done) {
-    set_error("internal: decode loop ended without reaching a stop condition (t=%d)", hst.t);
-    return M2M_ERR_STATE;
+  DecState hst = hsts[0];
+  for (int i = 0; i < nmb; ++i) {
+    if (n_steps > 0 && !hsts[i].done) {
+      set_error("internal: decode loop ended without reaching a stop condition (micro-batch %d, t=%d)", i, hsts[i].t);
+      return M2M_ERR_STATE;
+    }
+    // HF stops when ALL rows are finished: the batch length is the longest micro-batch
+    if (hsts[i].final_len > hst.final_len) hst.final_len = hsts[i].final_len;
+    if (hsts[i].t > hst.t) hst.t = hsts[i].t;
   }
   if (out_len) *out_len = hst.final_len;
   c->stats.decode_steps += hst.t;
@@ -760,9 +817,14 @@ int m2m_ctx_create(const m2m_config* cfg, int device, m2m_ctx** out) {
   c->device = device;
   c->num_sms = p.multiProcessorCount;
   memset(&c->stats, 0, sizeof(c->stats));
-  if (cudaMallocHost((void**)&c->h_done, sizeof(int)) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->poll_ev, cudaEventDisableTiming) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  bool ok = cudaMallocHost((void**)&c->h_done, MAX_MB * sizeof(int)) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < MAX_MB && ok; ++i)
+    ok = cudaEventCreateWithFlags(&c->poll_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&c->mb_streams[i], cudaStreamNonBlocking) == cudaSuccess;
+  if (const char* e = getenv("M2M_MICROBATCHES")) c->n_microbatch = std::max(1, std::min(MAX_MB, atoi(e)));
+  if (!ok) {
     set_error("context resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
     return M2M_ERR_CUDA;
@@ -775,7 +837,7 @@ int m2m_ctx_destroy(m2m_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+  for (auto ge : c->step_graphs) cudaGraphExecDestroy(ge);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
                     &c->enc_out, &c->ckv, &c->skv, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
@@ -783,7 +845,11 @@ int m2m_ctx_destroy(m2m_ctx* c) {
                     &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave, &c->host_cond, &c->host_tokens};
   for (DevBuf* b : bufs) b->release();
   if (c->h_done) cudaFreeHost(c->h_done);
-  if (c->poll_ev) cudaEventDestroy(c->poll_ev);
+  for (int i = 0; i < MAX_MB; ++i) {
+    if (c->poll_ev[i]) cudaEventDestroy(c->poll_ev[i]);
+    if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
+    if (c->mb_streams[i]) cudaStreamDestroy(c->mb_streams[i]);
+  }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return 0;

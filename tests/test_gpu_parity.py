@@ -143,12 +143,26 @@ def test_encoder_matches_oracle_other_lengths(engine_fp32, oracle_weights, repor
         assert err <= ENC_TOL
 
 
-def test_encoder_bf16(engine_bf16, cpu_embeds, report):
+def test_encoder_bf16(engine_bf16, cpu_embeds, oracle_weights, report):
+    """bf16 encoder with the fused tcgen05 attention and with the CUDA-core attention, several lengths."""
     g = golden("generate.npz")
-    out = engine_bf16.encode(cpu_embeds[g["enc_rows"].tolist()].to(DEV))
+    x = cpu_embeds[g["enc_rows"].tolist()].to(DEV)
+    out = engine_bf16.encode(x)
     err = norm_err(out, g["enc"])
-    report(test="encoder_bf16", norm_err=err)
-    assert err <= 5e-2
+    engine_bf16.set_flags(no_tc_attention=True)
+    out2 = engine_bf16.encode(x)
+    engine_bf16.set_flags()
+    err2 = norm_err(out2, g["enc"])
+    report(test="encoder_bf16", norm_err_tc_attention=err, norm_err_simt_attention=err2,
+           tc_vs_simt=norm_err(out, out2.cpu()))
+    assert err <= 2e-2 and err2 <= 2e-2
+    gen = torch.Generator().manual_seed(6)
+    for L in (1, 17, 64, 100, 129, 190, 256, 261):
+        xl = torch.randn(3, L, 384, generator=gen) * 3.0
+        ref = port.encoder(xl, oracle_weights)
+        e = norm_err(engine_bf16.encode(xl.to(DEV)), ref)
+        report(test="encoder_bf16_oracle", L=L, norm_err=e)
+        assert e <= 3e-2, (L, e)
 
 
 # ------------------------------------------------------------------------------ decode: logits
