@@ -116,6 +116,8 @@ struct m2m_ctx {
   cudaEvent_t join_ev[MAX_MB] = {};
   cudaStream_t mb_streams[MAX_MB] = {};
   cudaStream_t own_stream = nullptr;
+  int persist_blocks_per_sm = 4;
+  bool lean_gemm = false;  // set while capturing micro-batched decode steps
   int n_microbatch = 1;  // >1: independent decode chains on separate streams (M2M_MICROBATCHES); measured gain ~1 %
 
   std::vector<cudaGraphExec_t> step_graphs;  // one per micro-batch
@@ -150,7 +152,7 @@ static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K
   cudaError_t e;
   if constexpr (std::is_same<T, bf16>::value) {
     if (!(c->flags & 8u) && tc::supported(M, N, K, lda)) {
-      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms);
+      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms, c->lean_gemm);
       if (e != cudaSuccess) {
         set_error("tcgen05 gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
         return M2M_ERR_CUDA;
@@ -342,7 +344,8 @@ struct StepTiming {
 // others).
 template <typename T>
 static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, int max_length, const int64_t* forced,
-                              float* logits_all, bool skip_finished, StepTiming* tm, cudaStream_t s) {
+                              float* logits_all, bool skip_finished, StepTiming* tm, cudaStream_t s,
+                              bool persist = false) {
   const m2m_config& g = c->cfg;
   const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
   const int Tmax = max_length;  // cache positions per row
@@ -362,6 +365,7 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
   const size_t cross_layer = (size_t)B * L * 2 * I;
   constexpr bool FAST = !std::is_same<T, float>::value;
   dim3 agrid(g.n_heads, nb);
+  const unsigned pgrid = (unsigned)std::min<long>((long)c->num_sms * c->persist_blocks_per_sm, (long)nb * g.n_heads);
   for (int l = 0; l < g.n_layers; ++l) {
     const DecLayerW& w = c->dec[l];
     T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer + (size_t)r0 * Tmax * I;
@@ -372,15 +376,24 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, nb, 3 * I, D,
                     EpiQKVCache<T>{q, kc, vc, I, (size_t)Tmax * 64, (size_t)Tmax * I}, st, s));
     if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
-    decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
-                                                            c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
+    if (persist)
+      decode_attn_persist_kernel<T, true, FAST, 4><<<pgrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, (size_t)Tmax * 64,
+                                                                         0, c->dec_bias, g.max_positions, ao, g.n_heads,
+                                                                         nb, st, fin_skip);
+    else
+      decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
+                                                              c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
     LAUNCH_CHECK(c);
     if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, nb, D, I, EpiResidual{x, D}, st, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, nb, st, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, nb, I, D, EpiStore<T>{q, I}, st, s));
-    decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, cv, (size_t)L * I, (size_t)L * 64, L, nullptr, 0, ao,
-                                                             g.n_heads, st, fin_skip);
+    if (persist)
+      decode_attn_persist_kernel<T, false, FAST, 4><<<pgrid, 128, 0, s>>>(q, ck, cv, (size_t)L * I, (size_t)L * 64, L,
+                                                                          nullptr, 0, ao, g.n_heads, nb, st, fin_skip);
+    else
+      decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, cv, (size_t)L * I, (size_t)L * 64, L, nullptr, 0, ao,
+                                                               g.n_heads, st, fin_skip);
     LAUNCH_CHECK(c);
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, nb, D, I, EpiResidual{x, D}, st, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, nb, st, s));
@@ -449,7 +462,8 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   const bool skip_finished = (c->flags & 4u) && plain;
   // micro-batches: independent decode chains on their own streams (only for the plain, graph-replayed path)
   int nmb = 1;
-  if (use_graph && B >= 2 * 128) nmb = std::min<int>(c->n_microbatch, std::min(MAX_MB, B / 128));
+  const int want_mb = ((c->flags >> 8) & 0xF) ? (int)((c->flags >> 8) & 0xF) : c->n_microbatch;
+  if (use_graph && B >= 2 * 128) nmb = std::min<int>(want_mb, std::min(MAX_MB, B / 128));
   if (nmb < 1) nmb = 1;
   int mb_r0[MAX_MB + 1];
   for (int i = 0; i <= nmb; ++i) mb_r0[i] = (int)((int64_t)B * i / nmb);
@@ -486,8 +500,10 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
         // captured); the instantiated graphs are launched on the micro-batch streams.
         cudaStream_t cs = c->own_stream;
         M2M_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        c->lean_gemm = nmb > 1;
         int rc = decode_step_launch<T>(c, B, mb_r0[i], mb_r0[i + 1] - mb_r0[i], i, L, max_length, nullptr, nullptr,
-                                       skip_finished, nullptr, cs);
+                                       skip_finished, nullptr, cs, nmb > 1);
+        c->lean_gemm = false;
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         c->graph_nodes = (size_t)(c->stats.kernel_launches - launches_before);
         c->stats.kernel_launches = launches_before;
@@ -824,6 +840,7 @@ int m2m_ctx_create(const m2m_config* cfg, int device, m2m_ctx** out) {
          cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaStreamCreateWithFlags(&c->mb_streams[i], cudaStreamNonBlocking) == cudaSuccess;
   if (const char* e = getenv("M2M_MICROBATCHES")) c->n_microbatch = std::max(1, std::min(MAX_MB, atoi(e)));
+  if (const char* e = getenv("M2M_PERSIST_BLOCKS")) c->persist_blocks_per_sm = std::max(1, std::min(8, atoi(e)));
   if (!ok) {
     set_error("context resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;

@@ -260,12 +260,17 @@ inline cudaError_t launch_cfg(const bf16* A, int lda, const bf16* W, int M, int 
   return cudaGetLastError();
 }
 
+// lean = smaller operand rings (65 / 73 KB of shared memory) so that a GEMM CTA fits on an SM next to the
+// persistent decode-attention blocks of the other micro-batch.
 template <typename Epi>
 inline cudaError_t launch(const bf16* A, int lda, const bf16* W, int M, int N, int K, Epi epi, const DecState* st,
-                          cudaStream_t stream, int num_sms) {
+                          cudaStream_t stream, int num_sms, bool lean = false) {
   long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
-  if (tiles128 >= num_sms) return launch_cfg<128, 3, Epi>(A, lda, W, M, N, K, epi, st, stream);
-  return launch_cfg<64, 4, Epi>(A, lda, W, M, N, K, epi, st, stream);
+  if (tiles128 >= num_sms)
+    return lean ? launch_cfg<128, 2, Epi>(A, lda, W, M, N, K, epi, st, stream)
+                : launch_cfg<128, 3, Epi>(A, lda, W, M, N, K, epi, st, stream);
+  return lean ? launch_cfg<64, 3, Epi>(A, lda, W, M, N, K, epi, st, stream)
+              : launch_cfg<64, 4, Epi>(A, lda, W, M, N, K, epi, st, stream);
 }
 
 }  // namespace tc

@@ -348,3 +348,22 @@ def test_transcribe_host_matches_device_api(engine_fp32):
     toks0, _ = engine_fp32.transcribe_host(wave.numpy(), None, 64, device_batch=8)
     dev0 = engine_fp32.generate(wave.to(DEV), torch.zeros_like(cond).to(DEV), 64).cpu().numpy()
     assert np.array_equal(toks0, dev0)
+
+
+# ------------------------------------------------------------------------------ micro-batched decode
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_microbatched_persistent_decode_is_bit_identical(engine_bf16, engine_fp32, precision):
+    """>= 256 rows: the decode loop may run as independent micro-batches (persistent attention kernel, lean GEMM
+    rings, one CUDA graph and stream each).  Same arithmetic in the same order -> identical tokens."""
+    eng = engine_bf16 if precision == "bf16" else engine_fp32
+    wave = torch.cat([syn.audio_noise(150, 31), syn.audio_tones(150, 31)]).to(DEV)
+    cond = (torch.arange(600).reshape(300, 2) % 3).to(DEV)
+    eng.set_flags(microbatches=1)
+    a = eng.generate(wave, cond, 40)
+    outs = []
+    for n in (2, 3):
+        eng.set_flags(microbatches=n)
+        outs.append(eng.generate(wave, cond, 40))
+    eng.set_flags()
+    for o in outs:
+        assert torch.equal(a, o)
