@@ -304,6 +304,33 @@ def run_ours(args):
                               "path": "tcgen05 split-bf16 (6 bf16 MMA products per fp32 product)" if args.precision == "bf16"
                               else "fp32 CUDA-core DFT"}}
 
+        # BASELINE.json configs[2]: encoder forward + teacher-forced decoder forward, bf16, batch 32 (inference-shape
+        # arithmetic of T5Transformer.forward, labels of length 1024, L_enc = 190)
+        try:
+            nb, ld = 32, 1024
+            dec_in = torch.randint(5, 333, (nb, ld), device=dev)
+            dec_in[:, 0] = 1
+            cz = torch.zeros(nb, 2, dtype=torch.int64, device=dev)
+
+            def fwd():
+                enc = eng.encode(eng.condition(eng.logmel(wave[:nb]), cz))
+                return eng.decoder_forward(enc, dec_in)
+
+            for _ in range(2):
+                fwd()
+            torch.cuda.synchronize()
+            m0.record()
+            for _ in range(5):
+                fwd()
+            m1.record()
+            torch.cuda.synchronize()
+            f_ms = m0.elapsed_time(m1) / 5
+            gflop = nb * (1.579 + 5.262 + 47.29)  # mel DFT + encoder + teacher-forced decoder, per segment
+            extra["teacher_forced_forward"] = {"batch": nb, "label_len": ld, "enc_len": 190, "ms": f_ms,
+                                               "tflops_algorithmic": gflop / f_ms, "dtype": args.precision}
+        except Exception as e:  # reported, never fatal for the headline
+            extra["teacher_forced_forward"] = {"error": str(e)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, ms, cores, sample = cpu_reference_run(args.ref_clips, 1, 0)

@@ -67,6 +67,7 @@ struct EncLayerW {
 struct DecLayerW {
   float *ln0, *ln1, *ln2;
   void *wqkv, *wo, *wcq, *wckv, *wco, *wi, *wffo;
+  bf16 *wqkv_ln, *wcq_ln, *wi_ln;  // bf16 contexts: norm weight folded in (W[n,k] * ln[k]) for the fused RMSNorm-GEMMs
 };
 
 constexpr int MAX_MB = 8;
@@ -98,6 +99,7 @@ struct m2m_ctx {
   float *enc_final_ln = nullptr, *dec_final_ln = nullptr, *shared = nullptr, *enc_bias = nullptr, *dec_bias = nullptr,
         *dec_bias_seq = nullptr;
   void* lm_head = nullptr;
+  bf16* lm_head_ln = nullptr;
   float *window = nullptr, *dft_basis = nullptr, *band_w = nullptr, *cond_emb = nullptr;
   int *band_start = nullptr, *band_len = nullptr, *cond_off = nullptr, *cond_rows = nullptr;
   int n_freq = 0, dft_rows = 0, max_band = 32, enc_bias_ld = 0;
@@ -108,7 +110,7 @@ struct m2m_ctx {
   int64_t generation = 0;
   DevBuf mel_power, mel_a3, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
   DevBuf ckv, skv;  // cross / self KV caches, all layers
-  DevBuf dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err;
+  DevBuf dec_xb, dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err;
   DevBuf tf_x, tf_h, tf_qkv, tf_ao, tf_g, tf_q;  // teacher-forced decoder
   DevBuf host_wave, host_cond, host_tokens;      // m2m_transcribe_host device staging
   int* h_done = nullptr;                         // pinned, one flag per micro-batch
@@ -164,6 +166,20 @@ static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K
   e = launch_gemm_simt(RowMajorA<T>{A, lda}, W, K, M, N, K, epi, st, s, c->num_sms);
   if (e != cudaSuccess) {
     set_error("gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
+    return M2M_ERR_CUDA;
+  }
+  c->stats.kernel_launches++;
+  return 0;
+}
+
+// fused RMSNorm + GEMM on tcgen05 (bf16 contexts, decode step): A = bf16 residual stream, W = ln-folded weights
+template <typename Epi>
+static int gemm_rms(m2m_ctx* c, const bf16* xb, const bf16* W_ln, int M, int N, int K, Epi epi, const DecState* st,
+                    cudaStream_t s) {
+  if (M == 0) return 0;
+  cudaError_t e = tc::launch_rms(xb, K, W_ln, M, N, K, c->cfg.ln_eps, epi, st, s, c->num_sms, c->lean_gemm);
+  if (e != cudaSuccess) {
+    set_error("fused rmsnorm-gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
     return M2M_ERR_CUDA;
   }
   c->stats.kernel_launches++;
@@ -366,44 +382,82 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
   constexpr bool FAST = !std::is_same<T, float>::value;
   dim3 agrid(g.n_heads, nb);
   const unsigned pgrid = (unsigned)std::min<long>((long)c->num_sms * c->persist_blocks_per_sm, (long)nb * g.n_heads);
+  // bf16 contexts on tcgen05: RMSNorm is fused into the consuming GEMM (no rmsnorm launches, no h buffer)
+  bool fuse = false;
+  bf16* xb = nullptr;
+  if constexpr (std::is_same<T, bf16>::value) {
+    fuse = !(c->flags & 8u) && !(c->flags & 128u) && D % tc::BK == 0;
+    xb = c->dec_xb.as<bf16>() + (size_t)r0 * D;
+  }
+  auto attn = [&](bool self, const T* kp, const T* vp) -> int {
+    if (self) {
+      if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
+      if (persist)
+        decode_attn_persist_kernel<T, true, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64,
+                                                                           0, c->dec_bias, g.max_positions, ao,
+                                                                           g.n_heads, nb, st, fin_skip);
+      else
+        decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
+                                                                c->dec_bias, g.max_positions, ao, g.n_heads, st,
+                                                                fin_skip);
+      LAUNCH_CHECK(c);
+      if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
+    } else {
+      if (persist)
+        decode_attn_persist_kernel<T, false, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L,
+                                                                            nullptr, 0, ao, g.n_heads, nb, st, fin_skip);
+      else
+        decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr, 0,
+                                                                 ao, g.n_heads, st, fin_skip);
+      LAUNCH_CHECK(c);
+    }
+    return 0;
+  };
   for (int l = 0; l < g.n_layers; ++l) {
     const DecLayerW& w = c->dec[l];
     T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer + (size_t)r0 * Tmax * I;
     T* vc = kc + self_layer;
     const T* ck = c->ckv.as<T>() + (size_t)l * cross_layer + (size_t)r0 * L * I;
     const T* cv = ck + (size_t)B * L * I;
+    const EpiQKVCache<T> epi_qkv{q, kc, vc, I, (size_t)Tmax * 64, (size_t)Tmax * I};
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (fuse) {
+        M2M_TRY(gemm_rms(c, xb, w.wqkv_ln, nb, 3 * I, D, epi_qkv, st, s));
+        M2M_TRY(attn(true, kc, vc));
+        M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, nb, D, I, EpiResidualDual{x, xb, D}, st, s));
+        M2M_TRY(gemm_rms(c, xb, w.wcq_ln, nb, I, D, EpiStore<T>{q, I}, st, s));
+        M2M_TRY(attn(false, ck, cv));
+        M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, nb, D, I, EpiResidualDual{x, xb, D}, st, s));
+        M2M_TRY(gemm_rms(c, xb, w.wi_ln, nb, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
+        M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, nb, D, F, EpiResidualDual{x, xb, D}, st, s));
+        continue;
+      }
+    }
     M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, nb, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, nb, 3 * I, D,
-                    EpiQKVCache<T>{q, kc, vc, I, (size_t)Tmax * 64, (size_t)Tmax * I}, st, s));
-    if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
-    if (persist)
-      decode_attn_persist_kernel<T, true, FAST, 4><<<pgrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, (size_t)Tmax * 64,
-                                                                         0, c->dec_bias, g.max_positions, ao, g.n_heads,
-                                                                         nb, st, fin_skip);
-    else
-      decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kc, vc, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
-                                                              c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
-    LAUNCH_CHECK(c);
-    if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
+    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, nb, 3 * I, D, epi_qkv, st, s));
+    M2M_TRY(attn(true, kc, vc));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, nb, D, I, EpiResidual{x, D}, st, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, nb, st, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, nb, I, D, EpiStore<T>{q, I}, st, s));
-    if (persist)
-      decode_attn_persist_kernel<T, false, FAST, 4><<<pgrid, 128, 0, s>>>(q, ck, cv, (size_t)L * I, (size_t)L * 64, L,
-                                                                          nullptr, 0, ao, g.n_heads, nb, st, fin_skip);
-    else
-      decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, ck, cv, (size_t)L * I, (size_t)L * 64, L, nullptr, 0, ao,
-                                                               g.n_heads, st, fin_skip);
-    LAUNCH_CHECK(c);
+    M2M_TRY(attn(false, ck, cv));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, nb, D, I, EpiResidual{x, D}, st, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, nb, st, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, nb, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
     M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, nb, D, F, EpiResidual{x, D}, st, s));
   }
-  M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, nb, st, s));
-  M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, nb, V, D, EpiStore<float>{logits, V}, st, s));
+  bool head_done = false;
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (fuse) {
+      M2M_TRY(gemm_rms(c, xb, c->lm_head_ln, nb, V, D, EpiStore<float>{logits, V}, st, s));
+      head_done = true;
+    }
+  }
+  if (!head_done) {
+    M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, nb, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, nb, V, D, EpiStore<float>{logits, V}, st, s));
+  }
   select_token_kernel<<<nb, 128, 0, s>>>(logits, V, tokens, max_length, forced, fin, c->shared, x, D, logits_all, st,
-                                         g.pad_id, g.eos_id);
+                                         g.pad_id, g.eos_id, xb);
   LAUNCH_CHECK(c);
   step_advance_kernel<<<1, 1, 0, s>>>(st, forced == nullptr ? 1 : 0);
   LAUNCH_CHECK(c);
@@ -411,7 +465,7 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
 }
 
 __global__ void decode_init_kernel(int64_t* tokens, int ld, uint8_t* finished, float* x, const float* table, int D,
-                                   int B, int bos, DecState* st, int n_states, int max_length) {
+                                   int B, int bos, DecState* st, int n_states, int max_length, bf16* xb) {
   int b = blockIdx.x;
   if (threadIdx.x == 0) {
     tokens[(size_t)b * ld] = bos;
@@ -424,8 +478,14 @@ __global__ void decode_init_kernel(int64_t* tokens, int ld, uint8_t* finished, f
       st[b].max_length = max_length;
     }
   }
-  for (int i = threadIdx.x; i < D / 4; i += blockDim.x)
-    reinterpret_cast<float4*>(x + (size_t)b * D)[i] = reinterpret_cast<const float4*>(table + (size_t)bos * D)[i];
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(table + (size_t)bos * D)[i];
+    reinterpret_cast<float4*>(x + (size_t)b * D)[i] = v;
+    if (xb != nullptr) {
+      const float o[4] = {v.x, v.y, v.z, v.w};
+      store4(xb + (size_t)b * D + 4 * i, o);
+    }
+  }
 }
 
 template <typename T>
@@ -446,6 +506,7 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
 
   M2M_TRY(c->skv.ensure((size_t)g.n_layers * 2 * B * max_length * I * sizeof(T), &c->generation));
   M2M_TRY(c->dec_x.ensure((size_t)B * D * sizeof(float), &c->generation));
+  M2M_TRY(c->dec_xb.ensure((size_t)B * D * sizeof(bf16), &c->generation));
   M2M_TRY(c->dec_h.ensure((size_t)B * D * sizeof(T), &c->generation));
   M2M_TRY(c->dec_q.ensure((size_t)B * I * sizeof(T), &c->generation));
   M2M_TRY(c->dec_ao.ensure((size_t)B * I * sizeof(T), &c->generation));
@@ -472,7 +533,8 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   M2M_CUDA(cudaMemsetAsync(tokens, 0, (size_t)B * max_length * sizeof(int64_t), s));  // pad_id == 0 rows
   decode_init_kernel<<<B, 128, 0, s>>>(tokens, max_length, c->dec_finished.as<uint8_t>(),
                                                        c->dec_x.as<float>(), c->shared, D, B, g.bos_id,
-                                                       c->dec_state.as<DecState>(), nmb, max_length);
+                                                       c->dec_state.as<DecState>(), nmb, max_length,
+                                                       std::is_same<T, bf16>::value ? c->dec_xb.as<bf16>() : nullptr);
   LAUNCH_CHECK(c);
 
   StepTiming tm;
@@ -857,7 +919,7 @@ int m2m_ctx_destroy(m2m_ctx* c) {
   for (auto ge : c->step_graphs) cudaGraphExecDestroy(ge);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
-                    &c->enc_out, &c->ckv, &c->skv, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
+                    &c->enc_out, &c->ckv, &c->skv, &c->dec_xb, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
                     &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->tf_x, &c->tf_h,
                     &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave, &c->host_cond, &c->host_tokens};
   for (DevBuf* b : bufs) b->release();
@@ -909,7 +971,7 @@ int m2m_finalize_weights(m2m_ctx* c) {
   if (c->enc_lut.empty() || c->dec_lut.empty()) { set_error("finalize: bucket LUTs were never set"); return M2M_ERR_STATE; }
   ArenaBuilder ab;
   struct EncOff { size_t ln0, ln1, wqkv, wo, wi, wffo; };
-  struct DecOff { size_t ln0, ln1, ln2, wqkv, wo, wcq, wckv, wco, wi, wffo; };
+  struct DecOff { size_t ln0, ln1, ln2, wqkv, wo, wcq, wckv, wco, wi, wffo, wqkv_ln, wcq_ln, wi_ln; };
   std::vector<EncOff> eo(g.n_layers);
   std::vector<DecOff> dof(g.n_layers);
   const std::vector<float>* t = nullptr;
@@ -948,12 +1010,20 @@ int m2m_finalize_weights(m2m_ctx* c) {
   bool has_model = false;
   for (auto& kv : c->staged)
     if (kv.first.rfind("transformer.", 0) == 0) has_model = true;
+  size_t o_lm_ln = 0;
   size_t o_encfln = 0, o_decfln = 0, o_shared = 0, o_lm = 0, o_window = 0, o_encb = 0, o_decb = 0, o_decbs = 0;
   const int n_freq = g.n_fft / 2 + 1;
   const int enc_ld = 2 * g.max_enc_len - 1, enc_c = ((int)c->enc_lut.size() - 1) / 2;
   M2M_TRY(get_staged(c, "spectrogram.melspectrogram.spectrogram.window", g.n_fft, &t)); o_window = ab.push_f32(*t);
   if (has_model) {
   std::vector<float> tmp;
+  auto fold_ln = [&](std::vector<float> w, const char* ln_key, size_t* off) -> int {  // W[n,k] * ln[k], bf16
+    const std::vector<float>* ln = nullptr;
+    M2M_TRY(get_staged(c, ln_key, D, &ln));
+    for (size_t i = 0; i < w.size(); ++i) w[i] *= (*ln)[i % D];
+    *off = ab.push_typed(w, true);
+    return 0;
+  };
   for (int l = 0; l < g.n_layers; ++l) {
     M2M_TRY(one("transformer.encoder.block.%d.layer.0.%s.weight", l, "layer_norm", D, false, &eo[l].ln0));
     M2M_TRY(stack_rows("transformer.encoder.block.%d.layer.0.SelfAttention.%s.weight", l, {"q", "k", "v"}, I, D, tmp));
@@ -967,21 +1037,37 @@ int m2m_finalize_weights(m2m_ctx* c) {
     M2M_TRY(one("transformer.decoder.block.%d.layer.0.%s.weight", l, "layer_norm", D, false, &dof[l].ln0));
     M2M_TRY(stack_rows("transformer.decoder.block.%d.layer.0.SelfAttention.%s.weight", l, {"q", "k", "v"}, I, D, tmp));
     dof[l].wqkv = ab.push_typed(tmp, bf);
+    if (bf) {
+      snprintf(key, sizeof(key), "transformer.decoder.block.%d.layer.0.layer_norm.weight", l);
+      M2M_TRY(fold_ln(tmp, std::string(key).c_str(), &dof[l].wqkv_ln));
+    }
     M2M_TRY(one("transformer.decoder.block.%d.layer.0.SelfAttention.%s.weight", l, "o", (size_t)D * I, true, &dof[l].wo));
     M2M_TRY(one("transformer.decoder.block.%d.layer.1.%s.weight", l, "layer_norm", D, false, &dof[l].ln1));
     M2M_TRY(one("transformer.decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, "q", (size_t)I * D, true, &dof[l].wcq));
+    if (bf) {
+      snprintf(key, sizeof(key), "transformer.decoder.block.%d.layer.1.EncDecAttention.q.weight", l);
+      const std::vector<float>* wq = nullptr;
+      M2M_TRY(get_staged(c, key, (size_t)I * D, &wq));
+      snprintf(key, sizeof(key), "transformer.decoder.block.%d.layer.1.layer_norm.weight", l);
+      M2M_TRY(fold_ln(*wq, std::string(key).c_str(), &dof[l].wcq_ln));
+    }
     M2M_TRY(stack_rows("transformer.decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, {"k", "v"}, I, D, tmp));
     dof[l].wckv = ab.push_typed(tmp, bf);
     M2M_TRY(one("transformer.decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, "o", (size_t)D * I, true, &dof[l].wco));
     M2M_TRY(one("transformer.decoder.block.%d.layer.2.%s.weight", l, "layer_norm", D, false, &dof[l].ln2));
     M2M_TRY(interleave_wi("transformer.decoder.block.%d.layer.2.DenseReluDense.%s.weight", l, tmp));
     dof[l].wi = ab.push_typed(tmp, bf);
+    if (bf) {
+      snprintf(key, sizeof(key), "transformer.decoder.block.%d.layer.2.layer_norm.weight", l);
+      M2M_TRY(fold_ln(tmp, std::string(key).c_str(), &dof[l].wi_ln));
+    }
     M2M_TRY(one("transformer.decoder.block.%d.layer.2.DenseReluDense.%s.weight", l, "wo", (size_t)D * F, true, &dof[l].wffo));
   }
   M2M_TRY(get_staged(c, "transformer.encoder.final_layer_norm.weight", D, &t)); o_encfln = ab.push_f32(*t);
   M2M_TRY(get_staged(c, "transformer.decoder.final_layer_norm.weight", D, &t)); o_decfln = ab.push_f32(*t);
   M2M_TRY(get_staged(c, "transformer.shared.weight", (size_t)V * D, &t)); o_shared = ab.push_f32(*t);
   M2M_TRY(get_staged(c, "transformer.lm_head.weight", (size_t)V * D, &t)); o_lm = ab.push_typed(*t, bf);
+  if (bf) M2M_TRY(fold_ln(*t, "transformer.decoder.final_layer_norm.weight", &o_lm_ln));
 
   // relative-position bias LUTs (block 0 tables, shared by all blocks)
   std::vector<float> enc_bias((size_t)H * enc_ld), dec_bias((size_t)H * g.max_positions),
@@ -1108,12 +1194,16 @@ int m2m_finalize_weights(m2m_ctx* c) {
     c->enc[l] = EncLayerW{F32(eo[l].ln0), F32(eo[l].ln1), base + eo[l].wqkv, base + eo[l].wo, base + eo[l].wi,
                           base + eo[l].wffo};
     c->dec[l] = DecLayerW{F32(dof[l].ln0), F32(dof[l].ln1), F32(dof[l].ln2), base + dof[l].wqkv, base + dof[l].wo,
-                          base + dof[l].wcq, base + dof[l].wckv, base + dof[l].wco, base + dof[l].wi, base + dof[l].wffo};
+                          base + dof[l].wcq, base + dof[l].wckv, base + dof[l].wco, base + dof[l].wi, base + dof[l].wffo,
+                          bf ? reinterpret_cast<bf16*>(base + dof[l].wqkv_ln) : nullptr,
+                          bf ? reinterpret_cast<bf16*>(base + dof[l].wcq_ln) : nullptr,
+                          bf ? reinterpret_cast<bf16*>(base + dof[l].wi_ln) : nullptr};
   }
   c->enc_final_ln = F32(o_encfln);
   c->dec_final_ln = F32(o_decfln);
   c->shared = F32(o_shared);
   c->lm_head = base + o_lm;
+  c->lm_head_ln = bf ? reinterpret_cast<bf16*>(base + o_lm_ln) : nullptr;
   c->window = F32(o_window);
   c->enc_bias = F32(o_encb);
   c->enc_bias_ld = enc_ld;

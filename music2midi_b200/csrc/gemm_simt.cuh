@@ -64,6 +64,20 @@ struct EpiResidual {  // X[m, n] += v   (fp32 residual stream)
     *p = x;
   }
 };
+// X[m, n] += v and XB[m, n] = bf16(X[m, n]): the bf16 copy feeds the next fused RMSNorm-GEMM
+struct EpiResidualDual {
+  float* X;
+  bf16* XB;
+  int ld;
+  __device__ __forceinline__ void operator()(int m, int n, const float v[4], const DecState*) const {
+    float4* p = reinterpret_cast<float4*>(X + (size_t)m * ld + n);
+    float4 x = *p;
+    x.x += v[0]; x.y += v[1]; x.z += v[2]; x.w += v[3];
+    *p = x;
+    const float o[4] = {x.x, x.y, x.z, x.w};
+    store4(XB + (size_t)m * ld + n, o);
+  }
+};
 // W rows interleaved (2j = wi_0 row j, 2j+1 = wi_1 row j):  G[m, j] = gelu_new(c[2j]) * c[2j+1]
 template <typename TC>
 struct EpiGatedGelu {

@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(128) select_token_kernel(const float* __restri
                                                            uint8_t* __restrict__ finished,
                                                            const float* __restrict__ table, float* __restrict__ x, int D,
                                                            float* __restrict__ logits_out, DecState* __restrict__ st,
-                                                           int pad_id, int eos_id) {
+                                                           int pad_id, int eos_id, bf16* __restrict__ xb) {
   if (st->done) return;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int t = st->t;
@@ -559,7 +559,14 @@ __global__ void __launch_bounds__(128) select_token_kernel(const float* __restri
   __syncthreads();
   const float4* src = reinterpret_cast<const float4*>(table + (size_t)s_next * D);
   float4* dst = reinterpret_cast<float4*>(x + (size_t)b * D);
-  for (int i = tid; i < D / 4; i += 128) dst[i] = src[i];
+  for (int i = tid; i < D / 4; i += 128) {
+    const float4 v = src[i];
+    dst[i] = v;
+    if (xb != nullptr) {  // bf16 copy of the residual stream for the fused RMSNorm-GEMMs
+      const float o[4] = {v.x, v.y, v.z, v.w};
+      store4(xb + (size_t)b * D + 4 * i, o);
+    }
+  }
 }
 
 // advances the step counter; detects "all rows finished" / length cap.  <<<1,1>>>
