@@ -386,7 +386,7 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
   bool fuse = false;
   bf16* xb = nullptr;
   if constexpr (std::is_same<T, bf16>::value) {
-    fuse = !(c->flags & 8u) && !(c->flags & 128u) && D % tc::BK == 0;
+    fuse = !(c->flags & 8u) && (c->flags & 128u) && D % tc::BK == 0;  // opt-in: measured 2.4 % slower than the rmsnorm kernel
     xb = c->dec_xb.as<bf16>() + (size_t)r0 * D;
   }
   auto attn = [&](bool self, const T* kp, const T* vp) -> int {
@@ -902,6 +902,7 @@ int m2m_ctx_create(const m2m_config* cfg, int device, m2m_ctx** out) {
          cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaStreamCreateWithFlags(&c->mb_streams[i], cudaStreamNonBlocking) == cudaSuccess;
   if (const char* e = getenv("M2M_MICROBATCHES")) c->n_microbatch = std::max(1, std::min(MAX_MB, atoi(e)));
+  if (const char* e = getenv("M2M_FLAGS")) c->flags = (uint32_t)strtoul(e, nullptr, 0);  // A/B experiments
   if (const char* e = getenv("M2M_PERSIST_BLOCKS")) c->persist_blocks_per_sm = std::max(1, std::min(8, atoi(e)));
   if (!ok) {
     set_error("context resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
       rstd = rsqrtf(ss / (float)K + rms_eps);
+      // the transposition tiles below alias operand-ring stage 0: every epilogue warp must be done reading A
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -37,6 +37,14 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """Builds libm2m_b200.so if it is missing or older than its sources (nvcc cross-compiles without a GPU)."""
+    from music2midi_b200 import build
+
+    return build.build()
+
+
 @pytest.fixture(scope="session")
 def state_dict():
     from music2midi_b200 import synthetic as syn

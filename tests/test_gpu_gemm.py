@@ -61,7 +61,7 @@ def test_fused_rmsnorm_gemm_matches_unfused(engine_bf16, report):
     toks, lg = engine_bf16.generate_from_embeds(emb, 96, return_logits=True)
     forced = torch.zeros(4, 96, dtype=torch.long, device=DEV)
     forced[:, : toks.shape[1]] = toks
-    engine_bf16.set_flags(no_fused_rmsnorm=True)
+    engine_bf16.set_flags(fused_rmsnorm=True)  # experimental path, off by default (measured 2.4 % slower)
     _, lg2 = engine_bf16.generate_from_embeds(emb, 96, forced=forced, return_logits=True)
     engine_bf16.set_flags()
     d = (lg - lg2).abs()
