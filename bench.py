@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("M2M_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--clips", type=int, default=int(os.environ.get("M2M_BENCH_CLIPS", 256)), help="30 s clips per GPU")
-    ap.add_argument("--ref-clips", type=int, default=1, help="clips in the bounded CPU-reference sample")
+    ap.add_argument("--ref-clips", type=int, default=0,
+                    help="clips in the bounded CPU-reference sample (0 = largest batch that fits the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--max-length", type=int, default=MAX_LENGTH,
@@ -63,9 +64,11 @@ def workload_name(clips, max_length=MAX_LENGTH):
 
 
 # ------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_run(n_clips: int, steps: int, warmup: int):
+def cpu_reference_run(n_clips: int, steps: int, warmup: int, budget_s: float = 150.0):
     """The reference's CPU path (same torchaudio / HF calls as music2midi/transformer.py:41-45),
-    all host threads, bounded sample.  Returns (audio_s_per_s, ms_per_step, cores, sample string)."""
+    all host threads, bounded sample.  n_clips <= 0: pick the largest batch (up to 12 clips = 120 segments, the
+    reference chunks by inference.batch_size = 128 segments) whose (steps + warmup) full-length runs fit the time
+    budget, from a short calibration.  Returns (audio_s_per_s, ms_per_step, cores, sample string)."""
     import torch
 
     from music2midi_b200 import synthetic as syn
@@ -74,11 +77,24 @@ def cpu_reference_run(n_clips: int, steps: int, warmup: int):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     model = hf_path.build(syn.synthetic_state_dict(0))
+    with torch.no_grad():
+        model.generate(syn.audio_noise(2, 1), torch.zeros(2, 2, dtype=torch.long), max_length=8)  # library warm-up
+        if n_clips <= 0:
+            n_clips = 1
+            for cand in (12, 8, 4, 2):
+                w = syn.audio_noise(cand * SEGS_PER_CLIP, seed=99)
+                c = torch.zeros(cand * SEGS_PER_CLIP, 2, dtype=torch.long)
+                t0 = time.perf_counter()
+                model.generate(w, c, max_length=25)
+                per_token = (time.perf_counter() - t0) / 24
+                # late steps attend over a longer cache: measured ~1.7x the early-step cost at 1024 tokens
+                if per_token * 1.4 * (MAX_LENGTH - 1) * (steps + warmup) <= budget_s:
+                    n_clips = cand
+                    break
     n_seg = n_clips * SEGS_PER_CLIP
     wave = syn.audio_noise(n_seg, seed=100)
     cond = torch.zeros(n_seg, 2, dtype=torch.long)
     with torch.no_grad():
-        model.generate(wave[:2], cond[:2], max_length=8)  # library warm-up (lazy imports, thread pools)
         for _ in range(warmup):
             model.generate(wave, cond, max_length=MAX_LENGTH)
         times = []
@@ -333,7 +349,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, sample = cpu_reference_run(args.ref_clips, 1, 0)
+        v, ms, cores, sample = cpu_reference_run(args.ref_clips, 1, 0, budget_s=30.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_sample": ms}
 
     if world > 1:
