@@ -49,8 +49,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("M2M_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--clips", type=int, default=int(os.environ.get("M2M_BENCH_CLIPS", 256)), help="30 s clips per GPU")
-    ap.add_argument("--ref-clips", type=int, default=0,
-                    help="clips in the bounded CPU-reference sample (0 = largest batch that fits the time budget)")
+    ap.add_argument("--ref-clips", type=int, default=1,
+                    help="clips in the bounded CPU-reference sample (1 clip = 10 segments is the reference's own single-"
+                         "recording case and its best CPU throughput: 40 segments per batch measured 0.60 vs 0.88 "
+                         "audio-s/s on 8 cores); 0 = largest batch that fits the time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--max-length", type=int, default=MAX_LENGTH,

@@ -285,6 +285,7 @@ template <typename T>
 static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d_out, bool keep_typed, cudaStream_t s) {
   const m2m_config& g = c->cfg;
   M2M_REQUIRE(L >= 1 && L <= g.max_enc_len, "encoder length %d outside [1, %d]", L, g.max_enc_len);
+  M2M_REQUIRE(B <= 65535, "batch %d exceeds 65535 rows per call (chunk the batch)", B);
   if (B == 0) return 0;
   const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff;
   const size_t M = (size_t)B * L;
