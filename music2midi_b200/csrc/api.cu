@@ -254,9 +254,12 @@ static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_m
       return M2M_ERR_CUDA;
     }
     c->stats.kernel_launches++;
-    dim3 grid((g.d_model + 127) / 128, (unsigned)std::min<size_t>(rows, 4096));
-    mel_band_log_kernel<<<grid, 128, 0, s>>>(c->mel_power.as<float>(), ldp, c->band_start, c->band_len, c->band_w,
-                                             c->max_band, d_mel + r0 * g.d_model, rows, g.d_model);
+    M2M_REQUIRE(g.d_model <= 512, "mel_band_log: n_mels %d > 512 is not supported", g.d_model);
+    const unsigned bthreads = (unsigned)((g.d_model + 31) / 32 * 32);
+    const unsigned bblocks = (unsigned)std::min<size_t>(rows, (size_t)c->num_sms * 5);
+    mel_band_log_kernel<<<bblocks, bthreads, 2 * (size_t)ldp * sizeof(float), s>>>(
+        c->mel_power.as<float>(), ldp, c->band_start, c->band_len, c->band_w, c->max_band, d_mel + r0 * g.d_model, rows,
+        g.d_model);
     LAUNCH_CHECK(c);
   }
   return 0;
@@ -312,6 +315,18 @@ static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d
                                             g.max_enc_len - 1, s);
         if (e != cudaSuccess) {
           set_error("tcgen05 encoder attention launch failed: %s", cudaGetErrorString(e));
+          return M2M_ERR_CUDA;
+        }
+        c->stats.kernel_launches++;
+        attn_done = true;
+      }
+    }
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (!attn_done && !(c->flags & 64u)) {  // longer inputs (e.g. the 22.05 kHz training shape, L = 261): key-tiled kernel
+        cudaError_t e = tc::launch_seq_attn(qkv, 3 * I, B, L, g.n_heads, qkv, qkv, (uint64_t)M, 3 * I, I, 2 * I, 64, L, 0, L, ao,
+                                            I, c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, false, s);
+        if (e != cudaSuccess) {
+          set_error("tcgen05 tiled encoder attention launch failed: %s", cudaGetErrorString(e));
           return M2M_ERR_CUDA;
         }
         c->stats.kernel_launches++;
@@ -730,12 +745,39 @@ static int decoder_forward_impl(m2m_ctx* c, const float* d_enc, int B, int L, co
     const T* ck = c->ckv.as<T>() + (size_t)l * Me * 2 * I;
     M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
-    M2M_TRY((seq_attn<T, true>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)Ld * 3 * I, 64, 3 * I, ao, I, B, Ld, Ld,
-                               c->dec_bias_seq, 2 * g.max_positions - 1, g.max_positions - 1, s)));
+    bool tc_attn = false;
+    if constexpr (std::is_same<T, bf16>::value) tc_attn = !(c->flags & 64u);
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (tc_attn) {  // key-tiled fused tcgen05 attention, causal + bucket-bias LUT
+        cudaError_t e = tc::launch_seq_attn(qkv, 3 * I, B, Ld, g.n_heads, qkv, qkv, (uint64_t)M, 3 * I, I, 2 * I, 64, Ld, 0,
+                                            Ld, ao, I, c->dec_bias_seq, 2 * g.max_positions - 1, g.max_positions - 1,
+                                            true, s);
+        if (e != cudaSuccess) {
+          set_error("tcgen05 causal attention launch failed: %s", cudaGetErrorString(e));
+          return M2M_ERR_CUDA;
+        }
+        c->stats.kernel_launches++;
+      }
+    }
+    if (!tc_attn)
+      M2M_TRY((seq_attn<T, true>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)Ld * 3 * I, 64, 3 * I, ao, I, B, Ld, Ld,
+                                 c->dec_bias_seq, 2 * g.max_positions - 1, g.max_positions - 1, s)));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, (int)M, I, D, EpiStore<T>{q, I}, nullptr, s));
-    M2M_TRY((seq_attn<T, false>(c, q, I, ck, ck + Me * I, (size_t)L * I, L * 64, 64, ao, I, B, Ld, L, nullptr, 0, 0, s)));
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (tc_attn) {  // cross-attention over the head-major encoder K/V
+        cudaError_t e = tc::launch_seq_attn(q, I, B, Ld, g.n_heads, ck, ck + Me * I, (uint64_t)B * g.n_heads * L, 64, 0, 0, 0,
+                                            g.n_heads * L, L, L, ao, I, nullptr, 0, 0, false, s);
+        if (e != cudaSuccess) {
+          set_error("tcgen05 cross attention launch failed: %s", cudaGetErrorString(e));
+          return M2M_ERR_CUDA;
+        }
+        c->stats.kernel_launches++;
+      }
+    }
+    if (!tc_attn)
+      M2M_TRY((seq_attn<T, false>(c, q, I, ck, ck + Me * I, (size_t)L * I, L * 64, 64, ao, I, B, Ld, L, nullptr, 0, 0, s)));
     M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
     M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, M, nullptr, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));

@@ -163,6 +163,237 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Key-tiled fused attention on tcgen05 for long sequences (teacher-forced decoder: causal, up to 1024 keys; also
+// non-causal cross-attention over the encoder output).  One CTA per (128-query tile, head, batch row); keys are
+// processed in tiles of 128.  Two passes over the key tiles avoid any rescaling of the TMEM accumulator:
+//   pass 1: S = Q K_t^T (tensor core) -> row max of (S + bias) under the causal mask            (no exp, no V)
+//   pass 2: S again, P = exp(S + bias - max) as bf16 into the swizzled A-operand layout, O += P V_t in TMEM
+// The second QK^T costs 1/3 more tensor work on an otherwise idle pipe and removes the flash-attention
+// correction step.  Q/K/V tiles arrive by TMA (2-stage rings), every mbarrier wait is bounded.
+//   element (b, row, h, d) of Q at Q[(b*Lq + row)*ldq + h*64 + d] (tensor map tmQ, box 64x64)
+//   K/V: 2-D tensor maps over [rows_kv, ld_kv] with the (b, h) tile at column kv_col0 + h*64, row kv_row0(b) + j
+__global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                          const __grid_constant__ CUtensorMap tmK,
+                                                          const __grid_constant__ CUtensorMap tmV, int Lq, int Lk,
+                                                          int k_col0, int v_col0, int k_head_cols, int kv_rows_per_b,
+                                                          int kv_rows_per_h, bf16* __restrict__ O, int ldo,
+                                                          const float* __restrict__ bias, int bias_ld, int bias_zero,
+                                                          int causal) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                 // 16 KB
+  uint8_t* sK = sQ + 16384;           // 2 x 16 KB
+  uint8_t* sV = sK + 2 * 16384;       // 2 x 16 KB
+  uint8_t* sP = sV + 2 * 16384;       // 32 KB: 2 k-blocks of [128 x 64] bf16
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_empty, p_full, p_empty,
+      o_full;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nkeys = causal ? min(Lk, q0 + 128) : Lk;  // keys any query of this tile may attend to
+  const int nkt = (nkeys + 127) / 128;
+  const int kv_row0 = b * kv_rows_per_b + h * kv_rows_per_h;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(&s_full, 1);
+    mbar_init(&s_empty, 128);
+    mbar_init(&p_full, 128);
+    mbar_init(&p_empty, 1);
+    mbar_init(&o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_o = tmem_base;       // O: columns [0, 64)
+  const uint32_t tmem_s = tmem_base + 64;  // S: columns [64, 192)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_full, 16384u);
+      for (int r = 0; r < 2; ++r) tma_load_2d(sQ + r * 8192, &tmQ, &q_full, h * 64, b * Lq + q0 + 64 * r);
+      for (int it = 0; it < 2 * nkt; ++it) {
+        const int kt = it % nkt, st = it & 1;
+        mbar_wait(&k_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], 16384u);
+        for (int r = 0; r < 2; ++r)
+          tma_load_2d(sK + st * 16384 + r * 8192, &tmK, &k_full[st], k_col0 + h * k_head_cols, kv_row0 + kt * 128 + 64 * r);
+        if (it >= nkt) {
+          const int vi = it - nkt, vs = vi & 1;
+          mbar_wait(&v_empty[vs], ((vi >> 1) & 1) ^ 1);
+          mbar_expect_tx(&v_full[vs], 16384u);
+          for (int r = 0; r < 2; ++r)
+            tma_load_2d(sV + vs * 16384 + r * 8192, &tmV, &v_full[vs], v_col0 + h * k_head_cols, kv_row0 + kt * 128 + 64 * r);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128);
+      const uint32_t idesc_o = make_idesc(64) | (1u << 16);
+      mbar_wait(&q_full, 0);
+      const uint64_t qd = make_smem_desc(smem_u32(sQ));
+      for (int it = 0; it < 2 * nkt; ++it) {
+        const int st = it & 1;
+        mbar_wait(&k_full[st], (it >> 1) & 1);
+        mbar_wait(&s_empty, (it & 1) ^ 1);  // softmax warps finished reading the previous S
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t kd = make_smem_desc(smem_u32(sK + st * 16384));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma(tmem_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full);
+        if (it >= nkt) {
+          const int vi = it - nkt, vs = vi & 1;
+          mbar_wait(&v_full[vs], (vi >> 1) & 1);
+          mbar_wait(&p_full, vi & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t pd = make_smem_desc(smem_u32(sP) + (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u);
+            const uint64_t vd = make_smem_desc_mn(smem_u32(sV + vs * 16384) + (uint32_t)ks * 2048u, 16384u);
+            umma(tmem_o, pd, vd, idesc_o, (vi | ks) != 0);
+          }
+          umma_commit(&v_empty[vs]);
+          umma_commit(&p_empty);
+          if (vi == nkt - 1) umma_commit(&o_full);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int i = q0 + r;  // query position
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float* brow = (bias != nullptr) ? bias + (size_t)h * bias_ld + bias_zero - i : nullptr;
+    const int jmax = causal ? min(i, Lk - 1) : Lk - 1;  // last key visible to this query
+    float mx = -INFINITY, sum = 0.f;
+    const int rs = r & 7;
+    uint8_t* prow = sP + (size_t)(r >> 3) * 1024 + (size_t)rs * 128;
+    for (int it = 0; it < 2 * nkt; ++it) {
+      const int kt = it % nkt;
+      mbar_wait(&s_full, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (it < nkt) {  // pass 1: row max
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = kt * 128 + c0 + jj;
+            if (j <= jmax) mx = fmaxf(mx, __uint_as_float(v[jj]) + (brow ? __ldg(brow + j) : 0.f));
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&s_empty);
+      } else {  // pass 2: probabilities
+        const int vi = it - nkt;
+        mbar_wait(&p_empty, (vi & 1) ^ 1);  // previous PV MMAs have consumed P
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
+          float pbuf[32];
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = kt * 128 + c0 + jj;
+            pbuf[jj] = (j <= jmax) ? __expf(__uint_as_float(v[jj]) + (brow ? __ldg(brow + j) : 0.f) - mx) : 0.f;
+            sum += pbuf[jj];
+          }
+          uint8_t* pk = prow + (size_t)(c0 >> 6) * 16384;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const int chunk = ((c0 & 63) >> 3) + ch;
+            Vec16<bf16>::store(reinterpret_cast<bf16*>(pk + ((chunk ^ rs) << 4)), pbuf + 8 * ch);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&p_full);
+        mbar_arrive(&s_empty);
+      }
+    }
+    mbar_wait(&o_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float inv = 1.f / sum;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + lane_addr + (uint32_t)c0, v);
+      if (i < Lq) {
+        bf16* op = O + (size_t)(b * Lq + i) * ldo + h * 64 + c0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o8[e] = __uint_as_float(v[8 * ch + e]) * inv;
+          Vec16<bf16>::store(op + 8 * ch, o8);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+inline bool make_map_box64(CUtensorMap* tm, const bf16* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Q: [B*Lq, ldq] (head h at columns h*64).  K/V given as 2-D matrices: element (b, h, j, d) at row
+// b*kv_rows_per_b + h*kv_rows_per_h + j, column col0 + h*head_cols + d.
+//   packed qkv [B*L, 3I]   : rows_per_b = L, rows_per_h = 0, head_cols = 64, k_col0 = I, v_col0 = 2I
+//   head-major [b][h][j][64]: rows_per_b = H*L, rows_per_h = L, head_cols = 0, col0 = 0 (ld = 64)
+inline cudaError_t launch_seq_attn(const bf16* Q, int ldq, int B, int Lq, int H, const bf16* K, const bf16* V,
+                                   uint64_t kv_rows, int ld_kv, int k_col0, int v_col0, int head_cols, int rows_per_b,
+                                   int rows_per_h, int Lk, bf16* O, int ldo, const float* bias, int bias_ld,
+                                   int bias_zero, bool causal, cudaStream_t stream) {
+  CUtensorMap tq, tk, tv;
+  if (!make_map_box64(&tq, Q, (uint64_t)B * Lq, (uint64_t)ldq, (uint64_t)ldq) ||
+      !make_map_box64(&tk, K, kv_rows, (uint64_t)ld_kv, (uint64_t)ld_kv) ||
+      !make_map_box64(&tv, V, kv_rows, (uint64_t)ld_kv, (uint64_t)ld_kv))
+    return cudaErrorInvalidValue;
+  const int smem = 1024 + 16384 + 4 * 16384 + 32768;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(seq_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dim3 grid((Lq + 127) / 128, H, B);
+  seq_attn_tc_kernel<<<grid, 192, smem, stream>>>(tq, tk, tv, Lq, Lk, k_col0, v_col0, head_cols, rows_per_b, rows_per_h, O,
+                                                  ldo, bias, bias_ld, bias_zero, causal ? 1 : 0);
+  return cudaGetLastError();
+}
+
 inline bool enc_attn_supported(int L, int inner, int ld) { return L >= 1 && L <= 256 && inner % 64 == 0 && ld % 8 == 0; }
 
 // qkv: bf16 [B*L, ld] with columns [q (inner) | k (inner) | v (inner)]; O: bf16 [B*L, ldo]

@@ -633,24 +633,38 @@ __global__ void __launch_bounds__(256) frame_split_kernel(const float* __restric
 
 // ------------------------------------------------------------------ banded mel + clamp + log (a3)
 // out[m, j] = log(max(sum_i P[m, start[j] + i] * w[j][i], 1e-6)); the HTK filterbank is 0.5 % dense
-// (<= 14 taps per filter), so the projection is a banded gather, not a GEMM.
-__global__ void __launch_bounds__(128) mel_band_log_kernel(const float* __restrict__ P, int ldp,
+// (<= 14 taps per filter), so the projection is a banded gather, not a GEMM.  One thread per mel bin; each
+// power-spectrum row (4 KB, L2-resident) is staged in shared memory with coalesced 16-byte loads (double
+// buffered), taps are then read from shared memory; output rows are written fully coalesced.
+__global__ void __launch_bounds__(512) mel_band_log_kernel(const float* __restrict__ P, int ldp,
                                                            const int* __restrict__ start, const int* __restrict__ len,
                                                            const float* __restrict__ w, int max_band,
                                                            float* __restrict__ out, size_t rows, int n_mels) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_mels) return;
-  int s = start[j], n = len[j];
+  extern __shared__ __align__(16) float prow[];  // [2][ldp]
+  const int tid = threadIdx.x;
+  const int j = tid;
+  int s0 = 0, n = 0;
   float wv[32];
+  if (j < n_mels) {
+    s0 = start[j];
+    n = len[j];
+  }
 #pragma unroll
-  for (int i = 0; i < 32; ++i) wv[i] = (i < n) ? w[(size_t)j * max_band + i] : 0.f;
-  for (size_t m = blockIdx.y; m < rows; m += gridDim.y) {
-    const float* pr = P + m * ldp + s;
-    float acc = 0.f;
+  for (int i = 0; i < 32; ++i) wv[i] = (j < n_mels && i < n) ? w[(size_t)j * max_band + i] : 0.f;
+  const int nvec = ldp >> 2;
+  int buf = 0;
+  for (size_t m = blockIdx.x; m < rows; m += gridDim.x, buf ^= 1) {
+    float* pr = prow + (size_t)buf * ldp;
+    const float4* src = reinterpret_cast<const float4*>(P + m * ldp);
+    for (int i = tid; i < nvec; i += blockDim.x) reinterpret_cast<float4*>(pr)[i] = src[i];
+    __syncthreads();  // row staged; the other buffer is free again once everyone passed this barrier
+    if (j < n_mels) {
+      float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < n) acc = fmaf(__ldg(pr + i), wv[i], acc);
-    out[m * n_mels + j] = logf(fmaxf(acc, 1e-6f));
+      for (int i = 0; i < 32; ++i)
+        if (i < n) acc = fmaf(pr[s0 + i], wv[i], acc);
+      out[m * n_mels + j] = logf(fmaxf(acc, 1e-6f));
+    }
   }
 }
 

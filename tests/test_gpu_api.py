@@ -107,3 +107,22 @@ def test_long_teacher_forced_decoder_matches_oracle(engine_fp32, oracle_weights,
     d = float((out - ref).abs().max())
     report(test="decoder_forward_long_fp32", Ld=700, max_abs=d)
     assert d <= 2e-3
+
+
+@pytest.mark.parametrize("Ld", [1, 100, 128, 129, 700, 1024])
+def test_bf16_teacher_forced_decoder_tcgen05_attention(engine_bf16, oracle_weights, report, Ld):
+    """bf16 teacher-forced decoder: key-tiled fused tcgen05 attention (causal self-attention with the bucket-bias
+    LUT, cross-attention over head-major encoder K/V) against the fp32 oracle and against the CUDA-core kernel."""
+    g = torch.Generator().manual_seed(10 + Ld)
+    enc = torch.randn(2, 190, 384, generator=g)
+    dec_in = torch.randint(0, 400, (2, Ld), generator=g)
+    dec_in[:, 0] = 1
+    ref = port.decoder(dec_in, enc, oracle_weights)
+    out = engine_bf16.decoder_forward(enc.to(DEV), dec_in.to(DEV)).cpu()
+    engine_bf16.set_flags(no_tc_attention=True)
+    out2 = engine_bf16.decoder_forward(enc.to(DEV), dec_in.to(DEV)).cpu()
+    engine_bf16.set_flags()
+    d, d2 = (out - ref).abs(), (out2 - ref).abs()
+    report(test="decoder_forward_bf16", Ld=Ld, tc_max=float(d.max()), tc_mean=float(d.mean()), simt_max=float(d2.max()),
+           simt_mean=float(d2.mean()), tc_vs_simt_max=float((out - out2).abs().max()))
+    assert float(d.max()) <= 0.25 and float(d.mean()) <= 0.04
