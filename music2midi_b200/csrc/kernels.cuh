@@ -241,14 +241,15 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
   }
   __syncthreads();
 
+  const uint64_t pol = l2_evict_first_policy();
   auto issue = [&](int i) {  // thread 0 only: start the copies of chunk i
     const int s = i % STAGES, u = i / STAGES;
     if (u > 0) mbar_wait(&empty_bar[s], (u - 1) & 1);
     const int nk = min(CH, nkeys - i * CH);
     const uint32_t bytes = (uint32_t)nk * 64u * (uint32_t)sizeof(T);
     mbar_expect_tx(&full_bar[s], 2 * bytes);
-    bulk_g2s(ring[s][0], kg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s]);
-    bulk_g2s(ring[s][1], vg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s]);
+    bulk_g2s_hint(ring[s][0], kg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s], pol);
+    bulk_g2s_hint(ring[s][1], vg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s], pol);
   };
   if (tid == 0)
     for (int i = 0; i < STAGES - 1 && i < nchunks; ++i) issue(i);
