@@ -119,6 +119,7 @@ struct m2m_ctx {
   cudaStream_t mb_streams[MAX_MB] = {};
   cudaStream_t own_stream = nullptr;
   int persist_blocks_per_sm = 4;
+  int attn_stages = 3;  // operand-ring depth of decode_attn_kernel (M2M_ATTN_STAGES = 3 | 4)
   bool lean_gemm = false;  // set while capturing micro-batched decode steps
   int n_microbatch = 1;  // >1: independent decode chains on separate streams (M2M_MICROBATCHES); measured gain ~1 %
 
@@ -412,6 +413,10 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
         decode_attn_persist_kernel<T, true, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64,
                                                                            0, c->dec_bias, g.max_positions, ao,
                                                                            g.n_heads, nb, st, fin_skip);
+      else if (c->attn_stages == 4)
+        decode_attn_kernel<T, true, FAST, 4><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
+                                                                   c->dec_bias, g.max_positions, ao, g.n_heads, st,
+                                                                   fin_skip);
       else
         decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
                                                                 c->dec_bias, g.max_positions, ao, g.n_heads, st,
@@ -422,6 +427,9 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
       if (persist)
         decode_attn_persist_kernel<T, false, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L,
                                                                             nullptr, 0, ao, g.n_heads, nb, st, fin_skip);
+      else if (c->attn_stages == 4)
+        decode_attn_kernel<T, false, FAST, 4><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr,
+                                                                    0, ao, g.n_heads, st, fin_skip);
       else
         decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr, 0,
                                                                  ao, g.n_heads, st, fin_skip);
@@ -946,6 +954,7 @@ int m2m_ctx_create(const m2m_config* cfg, int device, m2m_ctx** out) {
          cudaStreamCreateWithFlags(&c->mb_streams[i], cudaStreamNonBlocking) == cudaSuccess;
   if (const char* e = getenv("M2M_MICROBATCHES")) c->n_microbatch = std::max(1, std::min(MAX_MB, atoi(e)));
   if (const char* e = getenv("M2M_FLAGS")) c->flags = (uint32_t)strtoul(e, nullptr, 0);  // A/B experiments
+  if (const char* e = getenv("M2M_ATTN_STAGES")) c->attn_stages = atoi(e) == 4 ? 4 : 3;
   if (const char* e = getenv("M2M_PERSIST_BLOCKS")) c->persist_blocks_per_sm = std::max(1, std::min(8, atoi(e)));
   if (!ok) {
     set_error("context resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));

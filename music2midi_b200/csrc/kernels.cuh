@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) seq_attn_kernel(const T* __restrict__ Q, 
 //   SELF:  nkeys = st->t + 1 (the current token's K/V were written by the QKV GEMM epilogue),
 //          score += bias[h][t - j]   (decoder unidirectional bucket LUT, block 0's table)
 //   CROSS: nkeys fixed (encoder length), no bias.
-template <typename T, bool SELF, bool FAST_EXP>
+template <typename T, bool SELF, bool FAST_EXP, int STAGES = 3>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ q, const T* __restrict__ Kc,
                                                           const T* __restrict__ Vc, size_t row_stride,
                                                           size_t head_stride, int nkeys_fixed,
@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
   if (st->done) return;
   const int h = blockIdx.x, b = blockIdx.y;
   if (finished != nullptr && finished[b]) return;
-  constexpr int STAGES = 3;
   constexpr int CHUNK_BYTES = 4096;                    // per K and per V
   constexpr int CH = CHUNK_BYTES / (64 * (int)sizeof(T));  // keys per chunk: 32 (bf16) / 16 (fp32)
   constexpr int VEC = Vec16<T>::N;                     // elements per 16 B
