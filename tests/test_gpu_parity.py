@@ -367,3 +367,30 @@ def test_microbatched_persistent_decode_is_bit_identical(engine_bf16, engine_fp3
     eng.set_flags()
     for o in outs:
         assert torch.equal(a, o)
+
+
+# ------------------------------------------------------------------------------ full benchmark batch size
+def test_full_batch_2560_rows_match_reference_tokens(engine_fp32, report):
+    """BASELINE full size (2560 segments in one device batch): every row is one of the 16 golden inputs, placed
+    at shuffled positions; segments are independent, so each copy must reproduce the reference tokens exactly
+    (size-independent property: batch invariance + golden parity at the benchmark batch size)."""
+    g = golden("generate.npz")
+    wave, cond = candidate_inputs()
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    perm = torch.randperm(2560, generator=torch.Generator().manual_seed(1)) % 16
+    L = 48
+    out = engine_fp32.generate(wave[perm].to(DEV), cond[perm].to(DEV), L).cpu()
+    assert out.shape == (2560, L)
+    bad = (out != tokens[perm, :L]).any(dim=1)
+    report(test="full_batch_2560_fp32", mismatching_rows=int(bad.sum()))
+    assert not bool(bad.any())
+
+
+def test_bf16_batch_invariance_at_full_size(engine_bf16):
+    """bf16 throughput mode: a row's tokens do not depend on the batch it is decoded in (2560 vs 16 rows)."""
+    wave, cond = candidate_inputs()
+    perm = torch.randperm(2560, generator=torch.Generator().manual_seed(2)) % 16
+    L = 48
+    small = engine_bf16.generate(wave.to(DEV), cond.to(DEV), L).cpu()
+    big = engine_bf16.generate(wave[perm].to(DEV), cond[perm].to(DEV), L).cpu()
+    assert torch.equal(big, small[perm])
