@@ -273,23 +273,57 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
       Vec16<T>::load_shared(ks + kl * 64 + c * VEC, kv[it]);
       Vec16<T>::load_shared(vs + kl * 64 + c * VEC, vv[it]);
     }
+    if constexpr (FAST_EXP) {
+      // throughput mode: one online-softmax update per chunk slice (ITERS keys) instead of one per key:
+      // fewer exps and accumulator rescales (the kernel runs at ~75 % issue-slot utilisation)
+      float sc[ITERS];
+      float mc = -INFINITY;
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int j = i * CH + warp * SLICE + it * KPI + g;
-      float sc = 0.f;
+      for (int it = 0; it < ITERS; ++it) {
+        const int j = i * CH + warp * SLICE + it * KPI + g;
+        float d = 0.f;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) sc = fmaf(qv[e], kv[it][e], sc);
+        for (int e = 0; e < VEC; ++e) d = fmaf(qv[e], kv[it][e], d);
 #pragma unroll
-      for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-      if (j < nkeys) {  // lanes of invalid keys read stale shared memory: ignored
-        if (SELF) sc += __ldg(bh + (t - j));
-        const float mn = fmaxf(m, sc);
-        const float r = FAST_EXP ? __expf(m - mn) : expf(m - mn);  // m = -inf -> 0
-        const float pw = FAST_EXP ? __expf(sc - mn) : expf(sc - mn);
-        l = l * r + pw;
+        for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (SELF && j < nkeys) d += __ldg(bh + (t - j));
+        sc[it] = (j < nkeys) ? d : -INFINITY;  // lanes of invalid keys read stale shared memory: masked
+        mc = fmaxf(mc, sc[it]);
+      }
+      if (mc > -INFINITY) {
+        const float mn = fmaxf(m, mc);
+        const float r = __expf(m - mn);  // m = -inf -> 0
+        l *= r;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * r + pw * vv[it][e];
+        for (int e = 0; e < VEC; ++e) acc[e] *= r;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const float pw = __expf(sc[it] - mn);  // masked keys: exp(-inf) = 0
+          l += pw;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[e] = fmaf(pw, vv[it][e], acc[e]);
+        }
         m = mn;
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int j = i * CH + warp * SLICE + it * KPI + g;
+        float sc = 0.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) sc = fmaf(qv[e], kv[it][e], sc);
+#pragma unroll
+        for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        if (j < nkeys) {  // lanes of invalid keys read stale shared memory: ignored
+          if (SELF) sc += __ldg(bh + (t - j));
+          const float mn = fmaxf(m, sc);
+          const float r = expf(m - mn);  // m = -inf -> 0
+          const float pw = expf(sc - mn);
+          l = l * r + pw;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * r + pw * vv[it][e];
+          m = mn;
+        }
       }
     }
     __syncwarp();
