@@ -267,9 +267,11 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
     const T* ks = reinterpret_cast<const T*>(ring[s][0]);
     const T* vs = reinterpret_cast<const T*>(ring[s][1]);
     float kv[ITERS][VEC], vv[ITERS][VEC];
+    const int nvalid = min(CH, nkeys - i * CH);  // keys the bulk copy delivered into this stage
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-      const int kl = warp * SLICE + it * KPI + g;
+      // lanes past the end re-read the last valid key (finite data, probability forced to 0 below)
+      const int kl = min(warp * SLICE + it * KPI + g, nvalid - 1);
       Vec16<T>::load_shared(ks + kl * 64 + c * VEC, kv[it]);
       Vec16<T>::load_shared(vs + kl * 64 + c * VEC, vv[it]);
     }
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
         for (int e = 0; e < VEC; ++e) acc[e] *= r;
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-          const float pw = __expf(sc[it] - mn);  // masked keys: exp(-inf) = 0
+          const float pw = __expf(sc[it] - mn);  // masked keys: exp(-inf) = 0 times a finite (re-read) V row
           l += pw;
 #pragma unroll
           for (int e = 0; e < VEC; ++e) acc[e] = fmaf(pw, vv[it][e], acc[e]);
@@ -464,29 +466,62 @@ __global__ void __launch_bounds__(128) decode_attn_persist_kernel(const T* __res
       const T* ks = reinterpret_cast<const T*>(ring[s][0]);
       const T* vs = reinterpret_cast<const T*>(ring[s][1]);
       float kv[ITERS][VEC], vv[ITERS][VEC];
+      const int nvalid = min(CH, nkeys - i * CH);
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
-        const int kl = warp * SLICE + it * KPI + g;
+        const int kl = min(warp * SLICE + it * KPI + g, nvalid - 1);
         Vec16<T>::load_shared(ks + kl * 64 + c * VEC, kv[it]);
         Vec16<T>::load_shared(vs + kl * 64 + c * VEC, vv[it]);
       }
+      if constexpr (FAST_EXP) {  // same update as decode_attn_kernel (bit-identical results)
+        float sc[ITERS];
+        float mc = -INFINITY;
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int j = i * CH + warp * SLICE + it * KPI + g;
-        float sc = 0.f;
+        for (int it = 0; it < ITERS; ++it) {
+          const int j = i * CH + warp * SLICE + it * KPI + g;
+          float d = 0.f;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) sc = fmaf(qv[e], kv[it][e], sc);
+          for (int e = 0; e < VEC; ++e) d = fmaf(qv[e], kv[it][e], d);
 #pragma unroll
-        for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-        if (j < nkeys) {
-          if (SELF) sc += __ldg(bh + (t - j));
-          const float mn = fmaxf(m, sc);
-          const float r = FAST_EXP ? __expf(m - mn) : expf(m - mn);
-          const float pw = FAST_EXP ? __expf(sc - mn) : expf(sc - mn);
-          l = l * r + pw;
+          for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          if (SELF && j < nkeys) d += __ldg(bh + (t - j));
+          sc[it] = (j < nkeys) ? d : -INFINITY;
+          mc = fmaxf(mc, sc[it]);
+        }
+        if (mc > -INFINITY) {
+          const float mn = fmaxf(m, mc);
+          const float r = __expf(m - mn);
+          l *= r;
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * r + pw * vv[it][e];
+          for (int e = 0; e < VEC; ++e) acc[e] *= r;
+#pragma unroll
+          for (int it = 0; it < ITERS; ++it) {
+            const float pw = __expf(sc[it] - mn);
+            l += pw;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = fmaf(pw, vv[it][e], acc[e]);
+          }
           m = mn;
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const int j = i * CH + warp * SLICE + it * KPI + g;
+          float sc = 0.f;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) sc = fmaf(qv[e], kv[it][e], sc);
+#pragma unroll
+          for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+          if (j < nkeys) {
+            if (SELF) sc += __ldg(bh + (t - j));
+            const float mn = fmaxf(m, sc);
+            const float r = expf(m - mn);
+            const float pw = expf(sc - mn);
+            l = l * r + pw;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * r + pw * vv[it][e];
+            m = mn;
+          }
         }
       }
       __syncwarp();
