@@ -29,10 +29,13 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
                                                           int nkb, int NK, uint32_t tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Q and K are dead once S = Q K^T has completed, so P (nkb k-blocks x 16 KB, [128 rows x 64 keys] bf16 each) is
+  // written over them: 72 KB instead of 112 KB for L = 190 -> two CTAs per SM (TMEM allows two as well).
   uint8_t* sQ = smem;                    // 2 boxes x 8 KB
   uint8_t* sK = sQ + 16384;              // nkb boxes x 8 KB
-  uint8_t* sV = sK + (size_t)nkb * 8192;
-  uint8_t* sP = sV + (size_t)nkb * 8192;  // nkb k-blocks x 16 KB: [128 rows x 64 keys] bf16 each
+  uint8_t* sP = smem;                    // aliases Q + K (+ padding)
+  const size_t region_a = (size_t)nkb * 16384 > 16384 + (size_t)nkb * 8192 ? (size_t)nkb * 16384 : 16384 + (size_t)nkb * 8192;
+  uint8_t* sV = smem + region_a;         // nkb boxes x 8 KB
   __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, bar_p, bar_o;
   __shared__ uint32_t tmem_base_smem;
 
@@ -184,9 +187,9 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                 // 16 KB
   uint8_t* sK = sQ + 16384;           // 2 x 16 KB
-  uint8_t* sV = sK + 2 * 16384;       // 2 x 16 KB
-  uint8_t* sP = sV + 2 * 16384;       // 32 KB: 2 k-blocks of [128 x 64] bf16
-  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_empty, p_full, p_empty,
+  uint8_t* sV = sK + 2 * 16384;       // 16 KB (single buffer: 97 KB in total -> two CTAs per SM)
+  uint8_t* sP = sV + 16384;           // 32 KB: 2 k-blocks of [128 x 64] bf16
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, s_empty, p_full, p_empty,
       o_full;
   __shared__ uint32_t tmem_base_smem;
 
@@ -201,9 +204,9 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
     }
+    mbar_init(&v_full, 1);
+    mbar_init(&v_empty, 1);
     mbar_init(&s_full, 1);
     mbar_init(&s_empty, 128);
     mbar_init(&p_full, 128);
@@ -235,11 +238,11 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
         for (int r = 0; r < 2; ++r)
           tma_load_2d(sK + st * 16384 + r * 8192, &tmK, &k_full[st], k_col0 + h * k_head_cols, kv_row0 + kt * 128 + 64 * r);
         if (it >= nkt) {
-          const int vi = it - nkt, vs = vi & 1;
-          mbar_wait(&v_empty[vs], ((vi >> 1) & 1) ^ 1);
-          mbar_expect_tx(&v_full[vs], 16384u);
+          const int vi = it - nkt;
+          mbar_wait(&v_empty, (vi & 1) ^ 1);
+          mbar_expect_tx(&v_full, 16384u);
           for (int r = 0; r < 2; ++r)
-            tma_load_2d(sV + vs * 16384 + r * 8192, &tmV, &v_full[vs], v_col0 + h * k_head_cols, kv_row0 + kt * 128 + 64 * r);
+            tma_load_2d(sV + r * 8192, &tmV, &v_full, v_col0 + h * k_head_cols, kv_row0 + kt * 128 + 64 * r);
         }
       }
     }
@@ -260,17 +263,17 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
         umma_commit(&k_empty[st]);
         umma_commit(&s_full);
         if (it >= nkt) {
-          const int vi = it - nkt, vs = vi & 1;
-          mbar_wait(&v_full[vs], (vi >> 1) & 1);
+          const int vi = it - nkt;
+          mbar_wait(&v_full, vi & 1);
           mbar_wait(&p_full, vi & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t pd = make_smem_desc(smem_u32(sP) + (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u);
-            const uint64_t vd = make_smem_desc_mn(smem_u32(sV + vs * 16384) + (uint32_t)ks * 2048u, 16384u);
+            const uint64_t vd = make_smem_desc_mn(smem_u32(sV) + (uint32_t)ks * 2048u, 16384u);
             umma(tmem_o, pd, vd, idesc_o, (vi | ks) != 0);
           }
-          umma_commit(&v_empty[vs]);
+          umma_commit(&v_empty);
           umma_commit(&p_empty);
           if (vi == nkt - 1) umma_commit(&o_full);
         }
@@ -381,7 +384,7 @@ inline cudaError_t launch_seq_attn(const bf16* Q, int ldq, int B, int Lq, int H,
       !make_map_box64(&tk, K, kv_rows, (uint64_t)ld_kv, (uint64_t)ld_kv) ||
       !make_map_box64(&tv, V, kv_rows, (uint64_t)ld_kv, (uint64_t)ld_kv))
     return cudaErrorInvalidValue;
-  const int smem = 1024 + 16384 + 4 * 16384 + 32768;
+  const int smem = 1024 + 16384 + 3 * 16384 + 32768;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(seq_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -413,7 +416,8 @@ inline cudaError_t launch_enc_attn(const bf16* qkv, int ld, int B, int L, int H,
   const int nkb = (L + 63) / 64;
   const int NK = (L + 15) / 16 * 16;
   const uint32_t tmem_cols = (64 + NK) <= 256 ? 256u : 512u;
-  const int smem = 1024 + 16384 + nkb * (8192 + 8192 + 16384);
+  const int region_a = nkb * 16384 > 16384 + nkb * 8192 ? nkb * 16384 : 16384 + nkb * 8192;
+  const int smem = 1024 + region_a + nkb * 8192;
   static int smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
