@@ -109,10 +109,14 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
     for (int c0 = 0; c0 < NK; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
+      const float* bp = brow + c0;
+      if (c0 + 32 <= L) {  // whole chunk valid (warp-uniform): no per-element predicates
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int j = c0 + jj;
-        if (j < L) mx = fmaxf(mx, __uint_as_float(v[jj]) + __ldg(brow + j));
+        for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, __uint_as_float(v[jj]) + __ldg(bp + jj));
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (c0 + jj < L) mx = fmaxf(mx, __uint_as_float(v[jj]) + __ldg(bp + jj));
       }
     }
     float sum = 0.f;
@@ -123,11 +127,19 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
       float p[32];
+      const float* bp = brow + c0;
+      if (c0 + 32 <= L) {
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int j = c0 + jj;
-        p[jj] = (j < L) ? __expf(__uint_as_float(v[jj]) + __ldg(brow + j) - mx) : 0.f;
-        sum += p[jj];
+        for (int jj = 0; jj < 32; ++jj) {
+          p[jj] = __expf(__uint_as_float(v[jj]) + __ldg(bp + jj) - mx);
+          sum += p[jj];
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          p[jj] = (c0 + jj < L) ? __expf(__uint_as_float(v[jj]) + __ldg(bp + jj) - mx) : 0.f;
+          sum += p[jj];
+        }
       }
       // 4 chunks of 8 keys -> 16-byte swizzled stores into k-block (c0 / 64)
       uint8_t* pk = prow + (size_t)(c0 >> 6) * 16384;
@@ -286,6 +298,7 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float* brow = (bias != nullptr) ? bias + (size_t)h * bias_ld + bias_zero - i : nullptr;
     const int jmax = causal ? min(i, Lk - 1) : Lk - 1;  // last key visible to this query
+    const int jmax_all = causal ? min(q0, Lk - 1) : Lk - 1;  // last key visible to EVERY query of this CTA
     float mx = -INFINITY, sum = 0.f;
     const int rs = r & 7;
     uint8_t* prow = sP + (size_t)(r >> 3) * 1024 + (size_t)rs * 128;
@@ -298,10 +311,22 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
+          const int jb = kt * 128 + c0;
+          if (jb + 31 <= jmax_all) {  // chunk visible to every query of this CTA (CTA-uniform): no predicates
+            if (brow) {
+              const float* bp = brow + jb;
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = kt * 128 + c0 + jj;
-            if (j <= jmax) mx = fmaxf(mx, __uint_as_float(v[jj]) + (brow ? __ldg(brow + j) : 0.f));
+              for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, __uint_as_float(v[jj]) + __ldg(bp + jj));
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, __uint_as_float(v[jj]));
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const int j = jb + jj;
+              if (j <= jmax) mx = fmaxf(mx, __uint_as_float(v[jj]) + (brow ? __ldg(brow + j) : 0.f));
+            }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -314,11 +339,29 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
           uint32_t v[32];
           tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
           float pbuf[32];
+          const int jb = kt * 128 + c0;
+          if (jb + 31 <= jmax_all) {
+            if (brow) {
+              const float* bp = brow + jb;
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = kt * 128 + c0 + jj;
-            pbuf[jj] = (j <= jmax) ? __expf(__uint_as_float(v[jj]) + (brow ? __ldg(brow + j) : 0.f) - mx) : 0.f;
-            sum += pbuf[jj];
+              for (int jj = 0; jj < 32; ++jj) {
+                pbuf[jj] = __expf(__uint_as_float(v[jj]) + __ldg(bp + jj) - mx);
+                sum += pbuf[jj];
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) {
+                pbuf[jj] = __expf(__uint_as_float(v[jj]) - mx);
+                sum += pbuf[jj];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const int j = jb + jj;
+              pbuf[jj] = (j <= jmax) ? __expf(__uint_as_float(v[jj]) + (brow ? __ldg(brow + j) : 0.f) - mx) : 0.f;
+              sum += pbuf[jj];
+            }
           }
           uint8_t* pk = prow + (size_t)(c0 >> 6) * 16384;
 #pragma unroll
