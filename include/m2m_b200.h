@@ -163,6 +163,7 @@ int m2m_stats_get(m2m_ctx* ctx, m2m_stats* out);
  * (default: tcgen05 in M2M_BF16 contexts, fp32 CUDA-core in M2M_FP32 contexts),
  * bit6 = use the CUDA-core sequence attention instead of the fused tcgen05 encoder attention,
  * bit7 = fuse RMSNorm into the decode-step tcgen05 GEMMs (bf16 contexts; experimental, measured slower),
+ * bit12 = programmatic dependent launch between the kernels of the decode step (bf16 contexts),
  * bits 8-11 = number of decode micro-batches (0 = context default). */
 int m2m_set_flags(m2m_ctx* ctx, uint32_t flags);
 

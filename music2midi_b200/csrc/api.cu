@@ -121,6 +121,7 @@ struct m2m_ctx {
   int persist_blocks_per_sm = 4;
   int attn_stages = 3;  // operand-ring depth of decode_attn_kernel (M2M_ATTN_STAGES = 3 | 4)
   bool lean_gemm = false;  // set while capturing micro-batched decode steps
+  bool pdl = false;        // set while launching a decode step with programmatic dependent launch
   int n_microbatch = 1;  // >1: independent decode chains on separate streams (M2M_MICROBATCHES); measured gain ~1 %
 
   std::vector<cudaGraphExec_t> step_graphs;  // one per micro-batch
@@ -155,7 +156,7 @@ static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K
   cudaError_t e;
   if constexpr (std::is_same<T, bf16>::value) {
     if (!(c->flags & 8u) && tc::supported(M, N, K, lda)) {
-      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms, c->lean_gemm);
+      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms, c->lean_gemm, c->pdl);
       if (e != cudaSuccess) {
         set_error("tcgen05 gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
         return M2M_ERR_CUDA;
@@ -192,8 +193,12 @@ static int rmsnorm(m2m_ctx* c, const float* x, const float* w, TO* y, size_t row
   if (rows == 0) return 0;
   int D = c->cfg.d_model;
   unsigned blocks = (unsigned)((rows + 7) / 8);
-  rmsnorm_kernel<TO><<<blocks, 256, 0, s>>>(x, w, y, (int)rows, D, c->cfg.ln_eps, st);
-  LAUNCH_CHECK(c);
+  cudaError_t le = launch_k(rmsnorm_kernel<TO>, dim3(blocks), dim3(256), 0, s, c->pdl, x, w, y, (int)rows, D, c->cfg.ln_eps, st);
+  if (le != cudaSuccess) {
+    set_error("rmsnorm launch failed: %s", cudaGetErrorString(le));
+    return M2M_ERR_CUDA;
+  }
+  c->stats.kernel_launches++;
   return 0;
 }
 
@@ -399,6 +404,13 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
   constexpr bool FAST = !std::is_same<T, float>::value;
   dim3 agrid(g.n_heads, nb);
   const unsigned pgrid = (unsigned)std::min<long>((long)c->num_sms * c->persist_blocks_per_sm, (long)nb * g.n_heads);
+  // programmatic dependent launch between the kernels of the step (bf16 / tcgen05 path only: every kernel launched
+  // with the attribute calls pdl_wait() before it touches upstream data)
+  struct PdlGuard {
+    m2m_ctx* c;
+    ~PdlGuard() { c->pdl = false; }
+  } pdl_guard{c};
+  c->pdl = std::is_same<T, bf16>::value && (c->flags & 4096u) && !(c->flags & 8u) && !persist && !(tm && tm->on);
   // bf16 contexts on tcgen05: RMSNorm is fused into the consuming GEMM (no rmsnorm launches, no h buffer)
   bool fuse = false;
   bf16* xb = nullptr;
@@ -418,9 +430,9 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
                                                                    c->dec_bias, g.max_positions, ao, g.n_heads, st,
                                                                    fin_skip);
       else
-        decode_attn_kernel<T, true, FAST><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
-                                                                c->dec_bias, g.max_positions, ao, g.n_heads, st,
-                                                                fin_skip);
+        (void)launch_k(decode_attn_kernel<T, true, FAST, 3>, agrid, dim3(128), 0, s, c->pdl, (const T*)q, kp, vp,
+                       (size_t)Tmax * I, (size_t)Tmax * 64, 0, (const float*)c->dec_bias, g.max_positions, ao, g.n_heads,
+                       (const DecState*)st, fin_skip);
       LAUNCH_CHECK(c);
       if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
     } else {
@@ -431,8 +443,9 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
         decode_attn_kernel<T, false, FAST, 4><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr,
                                                                     0, ao, g.n_heads, st, fin_skip);
       else
-        decode_attn_kernel<T, false, FAST><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr, 0,
-                                                                 ao, g.n_heads, st, fin_skip);
+        (void)launch_k(decode_attn_kernel<T, false, FAST, 3>, agrid, dim3(128), 0, s, c->pdl, (const T*)q, kp, vp,
+                       (size_t)L * I, (size_t)L * 64, L, (const float*)nullptr, 0, ao, g.n_heads, (const DecState*)st,
+                       fin_skip);
       LAUNCH_CHECK(c);
     }
     return 0;
@@ -480,10 +493,10 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
     M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, nb, st, s));
     M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, nb, V, D, EpiStore<float>{logits, V}, st, s));
   }
-  select_token_kernel<<<nb, 128, 0, s>>>(logits, V, tokens, max_length, forced, fin, c->shared, x, D, logits_all, st,
-                                         g.pad_id, g.eos_id, xb);
+  (void)launch_k(select_token_kernel, dim3(nb), dim3(128), 0, s, c->pdl, (const float*)logits, V, tokens, max_length, forced,
+                 fin, (const float*)c->shared, x, D, logits_all, st, g.pad_id, g.eos_id, xb);
   LAUNCH_CHECK(c);
-  step_advance_kernel<<<1, 1, 0, s>>>(st, forced == nullptr ? 1 : 0);
+  (void)launch_k(step_advance_kernel, dim3(1), dim3(1), 0, s, c->pdl, st, forced == nullptr ? 1 : 0);
   LAUNCH_CHECK(c);
   return 0;
 }

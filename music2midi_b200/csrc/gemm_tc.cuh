@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                                                       int a_split_rows, int w_split_rows, float rms_eps, Epi epi,
                                                       const DecState* __restrict__ st) {
   static_assert(!RMS || NSPLIT == 1, "fused RMSNorm needs plain bf16 operands");
-  if (st != nullptr && st->done) return;
   using L = SmemLayout<BN, STAGES, NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -121,11 +120,20 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) touches no global data and may overlap the
+  // tail of the previous kernel under programmatic dependent launch; everything below depends on it.
+  pdl_wait();
+  pdl_trigger();
+  const bool active = !(st != nullptr && st->done);  // finished decode: skip the work, still release TMEM
 
-  if (warp == 0) {
+  if (!active) {
+    // nothing to do
+  } else if (warp == 0) {
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -274,7 +282,8 @@ inline bool supported(int M, int N, int K, int lda) {
 // NSPLIT = 3: A is [3 * a_split_rows, K] and W is [3 * w_split_rows, K] (terms stacked along rows).
 template <int BN, int STAGES, typename Epi, int NSPLIT = 1, bool RMS = false>
 inline cudaError_t launch_cfg(const bf16* A, int lda, const bf16* W, int M, int N, int K, Epi epi, const DecState* st,
-                              cudaStream_t stream, int a_split_rows = 0, int w_split_rows = 0, float rms_eps = 0.f) {
+                              cudaStream_t stream, int a_split_rows = 0, int w_split_rows = 0, float rms_eps = 0.f,
+                              bool pdl = false) {
   CUtensorMap ta, tw;
   const uint64_t a_rows = NSPLIT == 1 ? (uint64_t)M : (uint64_t)NSPLIT * a_split_rows;
   const uint64_t w_rows = NSPLIT == 1 ? (uint64_t)N : (uint64_t)NSPLIT * w_split_rows;
@@ -289,21 +298,21 @@ inline cudaError_t launch_cfg(const bf16* A, int lda, const bf16* W, int M, int 
     attr_set = true;
   }
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  kern<<<grid, 192, smem, stream>>>(ta, tw, M, N, K, a_split_rows, w_split_rows, rms_eps, epi, st);
-  return cudaGetLastError();
+  return launch_k(kern, grid, dim3(192), (size_t)smem, stream, pdl, ta, tw, M, N, K, a_split_rows, w_split_rows, rms_eps,
+                  epi, st);
 }
 
 // lean = smaller operand rings (65 / 73 KB of shared memory) so that a GEMM CTA fits on an SM next to the
 // persistent decode-attention blocks of the other micro-batch.
 template <typename Epi>
 inline cudaError_t launch(const bf16* A, int lda, const bf16* W, int M, int N, int K, Epi epi, const DecState* st,
-                          cudaStream_t stream, int num_sms, bool lean = false) {
+                          cudaStream_t stream, int num_sms, bool lean = false, bool pdl = false) {
   long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
   if (tiles128 >= num_sms)
-    return lean ? launch_cfg<128, 2, Epi>(A, lda, W, M, N, K, epi, st, stream)
-                : launch_cfg<128, 3, Epi>(A, lda, W, M, N, K, epi, st, stream);
-  return lean ? launch_cfg<64, 3, Epi>(A, lda, W, M, N, K, epi, st, stream)
-              : launch_cfg<64, 4, Epi>(A, lda, W, M, N, K, epi, st, stream);
+    return lean ? launch_cfg<128, 2, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl)
+                : launch_cfg<128, 3, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl);
+  return lean ? launch_cfg<64, 3, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl)
+              : launch_cfg<64, 4, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl);
 }
 
 // fused RMSNorm + GEMM (K == d_model): A = bf16 residual stream, W = weights with the norm weight folded in

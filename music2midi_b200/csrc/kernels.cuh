@@ -15,6 +15,8 @@ template <typename TO>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       TO* __restrict__ y, int rows, int D, float eps,
                                                       const DecState* __restrict__ st) {
+  pdl_wait();
+  pdl_trigger();
   if (st != nullptr && st->done) return;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -206,6 +208,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
                                                           T* __restrict__ out, int H,
                                                           const DecState* __restrict__ st,
                                                           const uint8_t* __restrict__ finished) {
+  pdl_wait();  // everything below depends on the previous kernels of the step (q, the appended K/V row, DecState)
+  pdl_trigger();
   if (st->done) return;
   const int h = blockIdx.x, b = blockIdx.y;
   if (finished != nullptr && finished[b]) return;
@@ -591,6 +595,8 @@ __global__ void __launch_bounds__(128) select_token_kernel(const float* __restri
                                                            const float* __restrict__ table, float* __restrict__ x, int D,
                                                            float* __restrict__ logits_out, DecState* __restrict__ st,
                                                            int pad_id, int eos_id, bf16* __restrict__ xb) {
+  pdl_wait();
+  pdl_trigger();
   if (st->done) return;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int t = st->t;
@@ -640,6 +646,8 @@ __global__ void __launch_bounds__(128) select_token_kernel(const float* __restri
 
 // advances the step counter; detects "all rows finished" / length cap.  <<<1,1>>>
 __global__ void step_advance_kernel(DecState* st, int greedy_stop) {
+  pdl_wait();
+  pdl_trigger();
   if (st->done) return;
   int t = st->t + 1;  // tokens generated so far = t (excluding BOS) -> sequence length t + 1
   st->t = t;

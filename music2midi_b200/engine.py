@@ -214,10 +214,10 @@ class Engine:
     # ------------------------------------------------------------------ introspection
     def set_flags(self, graph: bool = True, time_attention: bool = False, skip_finished: bool = True,
                   no_tensor_cores: bool = False, mel: str = "auto", no_tc_attention: bool = False,
-                  microbatches: int = 0, fused_rmsnorm: bool = False):
+                  microbatches: int = 0, fused_rmsnorm: bool = False, pdl: bool = False):
         """mel: "auto" (tcgen05 DFT in bf16 contexts, fp32 CUDA-core DFT in fp32 contexts), "simt" or "tc"."""
         f = (1 if graph else 0) | (2 if time_attention else 0) | (4 if skip_finished else 0) | (8 if no_tensor_cores else 0)
-        f |= {"auto": 0, "simt": 16, "tc": 32}[mel] | (64 if no_tc_attention else 0) | ((microbatches & 0xF) << 8) | (128 if fused_rmsnorm else 0)
+        f |= {"auto": 0, "simt": 16, "tc": 32}[mel] | (64 if no_tc_attention else 0) | ((microbatches & 0xF) << 8) | (128 if fused_rmsnorm else 0) | (4096 if pdl else 0)
         check(self.lib.m2m_set_flags(self._ctx, f))
 
     def stats(self, reset: bool = False) -> Dict[str, float]:

@@ -419,3 +419,18 @@ def test_generate_batch_sizes(engine_fp32, cpu_embeds, batch):
     idx = torch.arange(batch) % 16
     out = engine_fp32.generate_from_embeds(cpu_embeds[idx].to(DEV), 20).cpu()
     assert torch.equal(out, tokens[idx, :20])
+
+
+def test_programmatic_dependent_launch_is_bit_identical(engine_bf16, cpu_embeds):
+    """PDL between the kernels of the decode step (graph and plain launches) must not change a single token."""
+    wave = torch.cat([syn.audio_noise(150, 33), syn.audio_tones(150, 33)]).to(DEV)
+    cond = (torch.arange(600).reshape(300, 2) % 3).to(DEV)
+    engine_bf16.set_flags()
+    ref_small = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 300)
+    ref_big = engine_bf16.generate(wave, cond, 64)
+    for graph in (True, False):
+        engine_bf16.set_flags(graph=graph, pdl=True)
+        a = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 300)
+        b = engine_bf16.generate(wave, cond, 64)
+        engine_bf16.set_flags()
+        assert torch.equal(a, ref_small) and torch.equal(b, ref_big), f"graph={graph}"
