@@ -356,6 +356,18 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, ms, cores, sample = cpu_reference_run(args.ref_clips, 1, 0, budget_s=30.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_sample": ms}
+        try:  # BASELINE.json configs[1]: the reference's CPU feature extraction (torchaudio MelSpectrogram + log)
+            from oracle import hf_path
+
+            spec = hf_path.build().spectrogram
+            w = syn.audio_noise(640, seed=7)
+            spec(w[:64])
+            t0 = time.perf_counter()
+            spec(w)
+            dt = time.perf_counter() - t0
+            cpu["mel_only"] = {"segments": 640, "frames": 640 * 188, "ms": 1e3 * dt, "frames_per_s": 640 * 188 / dt}
+        except Exception as e:
+            cpu["mel_only"] = {"error": str(e)[:200]}
 
     if world > 1:
         dist.barrier()
