@@ -141,6 +141,49 @@ class Music2MIDI(nn.Module):
         return rows
 
     @torch.no_grad()
+    def generate_many(self, audios, cond_index: Optional[List[int]] = None, distributed: bool = False):
+        """Batch entry point (not in the reference, which transcribes one recording per call): transcribes a list
+        of recordings (float32 arrays at the model sample rate) as ONE device batch of independent 3 s segments and
+        returns one MIDI object per recording.  With ``distributed=True`` and an initialised ``torch.distributed``
+        process group, every rank passes the same list, clips are sharded clip-wise over the ranks and the token
+        streams are all-gathered (music2midi_b200/distributed.py)."""
+        from . import distributed as dist_mod
+
+        sr = self.config.model.sample_rate
+        dur = self.config.dataset.segment_duration
+        split = int(sr * dur)
+        counts, padded = [], []
+        for y in audios:
+            y = np.asarray(y, dtype=np.float32)
+            n = max(1, int(np.ceil(len(y) / split)))
+            padded.append(np.pad(y, (0, n * split - len(y)), "constant"))
+            counts.append(n)
+        if not padded:
+            return []
+        lo_clip, hi_clip = 0, len(padded)
+        if distributed and torch.distributed.is_initialized():
+            lo_clip, hi_clip = dist_mod.shard_range(len(padded), torch.distributed.get_rank(),
+                                                    torch.distributed.get_world_size())
+        local = padded[lo_clip:hi_clip]
+        if local:
+            wave = torch.from_numpy(np.concatenate(local)).to(self.device)
+            rows = self.generate_tokens(wave, split, cond_index, max_length=1024)
+            tok = torch.zeros(len(rows), 1024, dtype=torch.int16, device=self.device)
+            for i, r in enumerate(rows):
+                tok[i, : r.numel()] = r.to(torch.int16)
+        else:
+            tok = torch.zeros(0, 1024, dtype=torch.int16, device=self.device)
+        if distributed and torch.distributed.is_initialized():
+            tok = dist_mod.gather_tokens(tok, sum(counts))
+        tok = tok.to(torch.int64).cpu()
+        out, pos = [], 0
+        for n in counts:
+            notes = self.model.tokenizer.decode(tok[pos:pos + n], mode="sequential", duration_per_batch=dur)
+            out.append(numpy_to_midi(notes))
+            pos += n
+        return out
+
+    @torch.no_grad()
     def sample_tokens(self, waveform: torch.Tensor, split_size: int, split_duration: float,
                       cond_index: Optional[List[int]] = None) -> np.ndarray:
         """(N,4) float64 notes [onset_s, offset_s, pitch, velocity] of the whole recording."""

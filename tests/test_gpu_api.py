@@ -126,3 +126,17 @@ def test_bf16_teacher_forced_decoder_tcgen05_attention(engine_bf16, oracle_weigh
     report(test="decoder_forward_bf16", Ld=Ld, tc_max=float(d.max()), tc_mean=float(d.mean()), simt_max=float(d2.max()),
            simt_mean=float(d2.mean()), tc_vs_simt_max=float((out - out2).abs().max()))
     assert float(d.max()) <= 0.25 and float(d.mean()) <= 0.04
+
+
+def test_generate_many_equals_per_recording_generate(m2m):
+    """Batch entry point: several recordings of different lengths as one device batch == one call per recording."""
+    g = torch.Generator().manual_seed(77)
+    audios = [(0.1 * torch.randn(n, generator=g)).numpy() for n in (48000, 100000, 20000)]
+    many = m2m.generate_many(audios, cond_index=[1, 0])
+    assert len(many) == 3
+    for y, midi in zip(audios, many):
+        single = m2m.generate(audio_y=y, cond_index=[1, 0])
+        a = [(n.start, n.end, n.pitch, n.velocity) for n in midi.instruments[0].notes]
+        b = [(n.start, n.end, n.pitch, n.velocity) for n in single.instruments[0].notes]
+        assert a == b
+    assert m2m.generate_many([]) == []
