@@ -115,6 +115,24 @@ class T5Weights(nn.Module):
     def device(self) -> torch.device:
         return self.shared.weight.device
 
+    @torch.no_grad()
+    def generate(self, inputs_embeds: torch.Tensor = None, max_length: int = 20, **kwargs) -> torch.Tensor:
+        """HF-style entry used as ``model.transformer.generate(inputs_embeds=..., max_length=...)``
+        (reference transformer.py:44): greedy decoding from encoder input embeddings."""
+        if inputs_embeds is None:
+            raise ValueError("inputs_embeds is required (the reference never passes input_ids)")
+        if kwargs.pop("do_sample", False) or kwargs.pop("num_beams", 1) != 1:
+            raise NotImplementedError("only greedy decoding is implemented (the reference never samples)")
+        if "max_new_tokens" in kwargs:
+            max_length = int(kwargs.pop("max_new_tokens")) + 1
+        if kwargs:
+            raise TypeError(f"unsupported generate() arguments: {sorted(kwargs)}")
+        owner = getattr(self, "_owner_engine", None)
+        if owner is None:
+            raise RuntimeError("T5Weights.generate needs its owning T5Transformer (engine not attached)")
+        eng = owner()
+        return eng.generate_from_embeds(inputs_embeds.to(eng.device), int(max_length))
+
 
 def _t5_config(node) -> SimpleNamespace:
     d = dict(d_kv=64, num_heads=8, relative_attention_max_distance=128, layer_norm_epsilon=1e-6,
@@ -157,6 +175,7 @@ class T5Transformer(nn.Module):
         # the sub-modules share this model's context instead of building their own
         object.__setattr__(self.spectrogram, "_owner_engine", lambda: ref().engine())
         object.__setattr__(self.conditioning, "_owner_engine", lambda: ref().engine())
+        object.__setattr__(self.transformer, "_owner_engine", lambda: ref().engine())
         self.eval()
 
     # ------------------------------------------------------------------ engine management

@@ -67,6 +67,9 @@ def test_t5transformer_generate_kwargs(m2m):
     out = m2m.model.generate(mi, max_length=50)
     assert out.device.type == "cuda" and out.dtype == torch.int64 and torch.equal(out.cpu(), exp[:, :50])
     assert m2m.model.generate(mi).shape == (2, 20)  # HF default max_length
+    # the HF-style call of the reference (transformer.py:42-44) on the parameter container
+    emb = m2m.model.conditioning(m2m.model.spectrogram(mi.input_waveform), mi.cond_index)
+    assert torch.equal(m2m.model.transformer.generate(inputs_embeds=emb, max_length=50).cpu(), exp[:, :50])
     assert torch.equal(m2m.model.generate(mi, max_new_tokens=9).cpu(), exp[:, :10])
     # weights edited in place are picked up (engine re-upload keyed on parameter versions)
     with torch.no_grad():
