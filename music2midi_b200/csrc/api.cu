@@ -103,7 +103,6 @@ struct m2m_ctx {
   float *window = nullptr, *dft_basis = nullptr, *band_w = nullptr, *cond_emb = nullptr;
   int *band_start = nullptr, *band_len = nullptr, *cond_off = nullptr, *cond_rows = nullptr;
   int n_freq = 0, dft_rows = 0, max_band = 32, enc_bias_ld = 0;
-  int dec_bias_far = 0;  // first distance from which the decoder bucket LUT is constant
   bf16* dft_basis3 = nullptr;  // [3][basis_split_rows][n_fft] bf16: hi/mid/lo terms of the DFT basis (tcgen05 path)
   int basis_split_rows = 0;
 
@@ -424,30 +423,28 @@ static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, 
       if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
       if (persist)
         decode_attn_persist_kernel<T, true, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64,
-                                                                           0, c->dec_bias, g.max_positions,
-                                                                           c->dec_bias_far, ao, g.n_heads, nb, st,
-                                                                           fin_skip);
+                                                                           0, c->dec_bias, g.max_positions, ao,
+                                                                           g.n_heads, nb, st, fin_skip);
       else if (c->attn_stages == 4)
         decode_attn_kernel<T, true, FAST, 4><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
-                                                                   c->dec_bias, g.max_positions, c->dec_bias_far, ao,
-                                                                   g.n_heads, st, fin_skip);
+                                                                   c->dec_bias, g.max_positions, ao, g.n_heads, st,
+                                                                   fin_skip);
       else
         (void)launch_k(decode_attn_kernel<T, true, FAST, 3>, agrid, dim3(128), 0, s, c->pdl, (const T*)q, kp, vp,
-                       (size_t)Tmax * I, (size_t)Tmax * 64, 0, (const float*)c->dec_bias, g.max_positions, c->dec_bias_far,
-                       ao, g.n_heads, (const DecState*)st, fin_skip);
+                       (size_t)Tmax * I, (size_t)Tmax * 64, 0, (const float*)c->dec_bias, g.max_positions, ao, g.n_heads,
+                       (const DecState*)st, fin_skip);
       LAUNCH_CHECK(c);
       if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
     } else {
       if (persist)
         decode_attn_persist_kernel<T, false, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L,
-                                                                            nullptr, 0, 0, ao, g.n_heads, nb, st,
-                                                                            fin_skip);
+                                                                            nullptr, 0, ao, g.n_heads, nb, st, fin_skip);
       else if (c->attn_stages == 4)
         decode_attn_kernel<T, false, FAST, 4><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr,
-                                                                    0, 0, ao, g.n_heads, st, fin_skip);
+                                                                    0, ao, g.n_heads, st, fin_skip);
       else
         (void)launch_k(decode_attn_kernel<T, false, FAST, 3>, agrid, dim3(128), 0, s, c->pdl, (const T*)q, kp, vp,
-                       (size_t)L * I, (size_t)L * 64, L, (const float*)nullptr, 0, 0, ao, g.n_heads, (const DecState*)st,
+                       (size_t)L * I, (size_t)L * 64, L, (const float*)nullptr, 0, ao, g.n_heads, (const DecState*)st,
                        fin_skip);
       LAUNCH_CHECK(c);
     }
@@ -1277,11 +1274,6 @@ int m2m_finalize_weights(m2m_ctx* c) {
   c->enc_bias = F32(o_encb);
   c->enc_bias_ld = enc_ld;
   c->dec_bias = F32(o_decb);
-  {
-    int far = g.max_positions;
-    while (far > 0 && c->dec_lut[far - 1] == c->dec_lut[g.max_positions - 1]) --far;
-    c->dec_bias_far = far;  // 113 for T5's 32 buckets / max distance 128
-  }
   c->dec_bias_seq = F32(o_decbs);
   c->dft_basis = F32(o_basis);
   c->dft_basis3 = reinterpret_cast<bf16*>(base + o_basis3);

@@ -204,7 +204,7 @@ template <typename T, bool SELF, bool FAST_EXP, int STAGES = 3>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ q, const T* __restrict__ Kc,
                                                           const T* __restrict__ Vc, size_t row_stride,
                                                           size_t head_stride, int nkeys_fixed,
-                                                          const float* __restrict__ bias, int bias_ld, int bias_far,
+                                                          const float* __restrict__ bias, int bias_ld,
                                                           T* __restrict__ out, int H,
                                                           const DecState* __restrict__ st,
                                                           const uint8_t* __restrict__ finished) {
@@ -260,9 +260,6 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
   float qv[VEC];
   Vec16<T>::load(q + (size_t)b * inner + h * 64 + c * VEC, qv);
   const float* bh = SELF ? bias + (size_t)h * bias_ld : nullptr;
-  // the T5 bucket LUT is constant beyond distance bias_far (last bucket): chunks that lie entirely in that range
-  // use a register instead of one L1 load per key
-  const float bfar = SELF ? __ldg(bh + bias_ld - 1) : 0.f;
   float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
@@ -275,7 +272,6 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
     const T* vs = reinterpret_cast<const T*>(ring[s][1]);
     float kv[ITERS][VEC], vv[ITERS][VEC];
     const int nvalid = min(CH, nkeys - i * CH);  // keys the bulk copy delivered into this stage
-    const bool far = SELF && (t - (i * CH + CH - 1)) >= bias_far;  // whole chunk beyond the last bucket boundary
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       // lanes past the end re-read the last valid key (finite data, probability forced to 0 below)
@@ -296,7 +292,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
         for (int e = 0; e < VEC; ++e) d = fmaf(qv[e], kv[it][e], d);
 #pragma unroll
         for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (SELF && j < nkeys) d += far ? bfar : __ldg(bh + (t - j));
+        if (SELF && j < nkeys) d += __ldg(bh + (t - j));
         sc[it] = (j < nkeys) ? d : -INFINITY;  // lanes of invalid keys read stale shared memory: masked
         mc = fmaxf(mc, sc[it]);
       }
@@ -325,7 +321,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
 #pragma unroll
         for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
         if (j < nkeys) {  // lanes of invalid keys read stale shared memory: ignored
-          if (SELF) sc += far ? bfar : __ldg(bh + (t - j));
+          if (SELF) sc += __ldg(bh + (t - j));
           const float mn = fmaxf(m, sc);
           const float r = expf(m - mn);  // m = -inf -> 0
           const float pw = expf(sc - mn);
@@ -392,7 +388,7 @@ __global__ void __launch_bounds__(128) decode_attn_persist_kernel(const T* __res
                                                                   const T* __restrict__ Vc, size_t row_stride,
                                                                   size_t head_stride, int nkeys_fixed,
                                                                   const float* __restrict__ bias, int bias_ld,
-                                                                  int bias_far, T* __restrict__ out, int H, int nb,
+                                                                  T* __restrict__ out, int H, int nb,
                                                                   const DecState* __restrict__ st,
                                                                   const uint8_t* __restrict__ finished) {
   if (st->done) return;
@@ -463,7 +459,6 @@ __global__ void __launch_bounds__(128) decode_attn_persist_kernel(const T* __res
     float qv[VEC];
     Vec16<T>::load(q + (size_t)b * inner + h * 64 + c * VEC, qv);
     const float* bh = SELF ? bias + (size_t)h * bias_ld : nullptr;
-    const float bfar = SELF ? __ldg(bh + bias_ld - 1) : 0.f;
     float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
@@ -476,7 +471,6 @@ __global__ void __launch_bounds__(128) decode_attn_persist_kernel(const T* __res
       const T* vs = reinterpret_cast<const T*>(ring[s][1]);
       float kv[ITERS][VEC], vv[ITERS][VEC];
       const int nvalid = min(CH, nkeys - i * CH);
-      const bool far = SELF && (t - (i * CH + CH - 1)) >= bias_far;
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const int kl = min(warp * SLICE + it * KPI + g, nvalid - 1);
@@ -494,7 +488,7 @@ __global__ void __launch_bounds__(128) decode_attn_persist_kernel(const T* __res
           for (int e = 0; e < VEC; ++e) d = fmaf(qv[e], kv[it][e], d);
 #pragma unroll
           for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-          if (SELF && j < nkeys) d += far ? bfar : __ldg(bh + (t - j));
+          if (SELF && j < nkeys) d += __ldg(bh + (t - j));
           sc[it] = (j < nkeys) ? d : -INFINITY;
           mc = fmaxf(mc, sc[it]);
         }
@@ -523,7 +517,7 @@ __global__ void __launch_bounds__(128) decode_attn_persist_kernel(const T* __res
 #pragma unroll
           for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
           if (j < nkeys) {
-            if (SELF) sc += far ? bfar : __ldg(bh + (t - j));
+            if (SELF) sc += __ldg(bh + (t - j));
             const float mn = fmaxf(m, sc);
             const float r = expf(m - mn);
             const float pw = expf(sc - mn);
