@@ -152,19 +152,39 @@ typedef struct m2m_stats {
   double last_attn_ms;       /* CUDA-event time of the decode self-attention kernels, if timing on */
   double last_generate_ms;
   int64_t last_attn_launches;
-  int64_t attn_bytes;        /* algorithmic KV bytes read by the timed self+cross attention kernels */
+  int64_t attn_bytes;        /* algorithmic KV bytes read by the timed decode self-attention launches */
+  int64_t cross_attn_bytes;  /* algorithmic KV bytes read by the timed decode cross-attention launches */
+  /* instrumented pass (flag bit1): CUDA-event time and launch-group count per kernel class, indexed by
+   * m2m_kernel_class, of the last m2m_generate / m2m_generate_from_embeds call */
+  double class_ms[16];
+  int64_t class_launches[16];
 } m2m_stats;
+
+typedef enum m2m_kernel_class {
+  M2M_KC_MEL_FRAME = 0,  /* framing + window (+ 3-way bf16 split) */
+  M2M_KC_MEL_DFT = 1,    /* DFT-as-GEMM + power spectrum */
+  M2M_KC_MEL_BAND = 2,   /* banded mel projection + clamp + log */
+  M2M_KC_COND = 3,       /* conditioning gather / staging copies */
+  M2M_KC_ENC_NORM = 4,
+  M2M_KC_ENC_GEMM = 5,
+  M2M_KC_ENC_ATTN = 6,
+  M2M_KC_CROSS_KV = 7,
+  M2M_KC_DEC_SELF_ATTN = 8,
+  M2M_KC_DEC_CROSS_ATTN = 9,
+  M2M_KC_DEC_CHAIN = 10, /* decode-step GEMM chain (projections, FFN, norms, lm_head) */
+  M2M_KC_DEC_SELECT = 11 /* argmax / EOS / pad / embedding gather / step advance */
+} m2m_kernel_class;
 int m2m_stats_reset(m2m_ctx* ctx);
 int m2m_stats_get(m2m_ctx* ctx, m2m_stats* out);
-/* flags: bit0 = use CUDA graph for the decode step (default 1), bit1 = time attention kernels with
- * events (forces non-graph launches), bit2 = skip finished rows in attention (default 1),
+/* flags: bit0 = use CUDA graph for the decode step (default 1), bit1 = instrumented pass: every launch group
+ * is bracketed by CUDA events on the launching stream and summed per kernel class (forces non-graph launches,
+ * finished rows are not skipped), bit2 = skip finished rows in attention (default 1),
  * bit3 = route bf16 GEMMs to the CUDA-core kernel instead of tcgen05 (A/B testing),
  * bit4 = force the fp32 CUDA-core DFT in the log-mel frontend, bit5 = force the tcgen05 split-bf16 DFT
  * (default: tcgen05 in M2M_BF16 contexts, fp32 CUDA-core in M2M_FP32 contexts),
  * bit6 = use the CUDA-core sequence attention instead of the fused tcgen05 encoder attention,
- * bit7 = fuse RMSNorm into the decode-step tcgen05 GEMMs (bf16 contexts; experimental, measured slower),
- * bit12 = programmatic dependent launch between the kernels of the decode step (bf16 contexts),
- * bits 8-11 = number of decode micro-batches (0 = context default). */
+ * bit7 = bf16 contexts: run the decode step as separate RMSNorm / GEMM launches instead of the cluster-phased
+ * tcgen05 GEMM chain (A/B testing). */
 int m2m_set_flags(m2m_ctx* ctx, uint32_t flags);
 
 /* Test hook (tests/test_gpu_gemm.py): d_C fp32 [M,N] = A[M,K] . W[N,K]^T with bf16 device operands, through

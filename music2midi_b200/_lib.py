@@ -37,7 +37,13 @@ class Stats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_int64), ("decode_steps", C.c_int64), ("last_attn_ms", C.c_double),
         ("last_generate_ms", C.c_double), ("last_attn_launches", C.c_int64), ("attn_bytes", C.c_int64),
+        ("cross_attn_bytes", C.c_int64), ("class_ms", C.c_double * 16), ("class_launches", C.c_int64 * 16),
     ]
+
+
+# m2m_kernel_class (include/m2m_b200.h): index into Stats.class_ms / class_launches
+KERNEL_CLASSES = ("mel_frame", "mel_dft", "mel_band", "cond", "enc_norm", "enc_gemm", "enc_attn", "cross_kv",
+                  "dec_self_attn", "dec_cross_attn", "dec_chain", "dec_select")
 
 
 # every symbol include/m2m_b200.h declares: (restype, argtypes)

@@ -16,6 +16,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
+#include "chain_tc.cuh"
 #include "kernels.cuh"
 
 namespace m2m {
@@ -67,10 +68,28 @@ struct EncLayerW {
 struct DecLayerW {
   float *ln0, *ln1, *ln2;
   void *wqkv, *wo, *wcq, *wckv, *wco, *wi, *wffo;
-  bf16 *wqkv_ln, *wcq_ln, *wi_ln;  // bf16 contexts: norm weight folded in (W[n,k] * ln[k]) for the fused RMSNorm-GEMMs
+  // bf16 contexts: norm weight folded in (W'[n,k] = W[n,k] * ln[k]) for the decode-step GEMM chain (chain_tc.cuh);
+  // wcq_ln is zero-padded to 6 x 96 rows (one 96-row slice per CTA of the cluster)
+  bf16 *wqkv_ln, *wcq_ln, *wi_ln;
 };
 
-constexpr int MAX_MB = 8;
+// kernel classes of the hot path, timed separately in the instrumented pass (flag bit 1) for bench.py's
+// roofline_by_class
+enum KClass {
+  KC_MEL_FRAME = 0,   // framing + window (+ 3-way bf16 split)
+  KC_MEL_DFT,         // DFT-as-GEMM + power
+  KC_MEL_BAND,        // banded mel + clamp + log
+  KC_COND,            // conditioning gather / copies
+  KC_ENC_NORM,        // encoder RMSNorm kernels
+  KC_ENC_GEMM,        // encoder projections / FFN
+  KC_ENC_ATTN,        // encoder self-attention
+  KC_CROSS_KV,        // cross-attention K/V of all decoder layers
+  KC_DEC_SELF_ATTN,   // KV-cached decode self-attention
+  KC_DEC_CROSS_ATTN,  // decode cross-attention
+  KC_DEC_CHAIN,       // decode-step GEMM chain (+ norms)
+  KC_DEC_SELECT,      // argmax / EOS / embedding gather / step advance
+  KC_COUNT
+};
 
 struct GraphKey {
   int B = -1, L = -1, max_length = -1;
@@ -110,25 +129,26 @@ struct m2m_ctx {
   int64_t generation = 0;
   DevBuf mel_power, mel_a3, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
   DevBuf ckv, skv;  // cross / self KV caches, all layers
-  DevBuf dec_xb, dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err;
+  DevBuf dec_xb, dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err, dec_ss;
   DevBuf tf_x, tf_h, tf_qkv, tf_ao, tf_g, tf_q;  // teacher-forced decoder
-  DevBuf host_wave, host_cond, host_tokens;      // m2m_transcribe_host device staging
-  int* h_done = nullptr;                         // pinned, one flag per micro-batch
-  cudaEvent_t poll_ev[MAX_MB] = {};
-  cudaEvent_t join_ev[MAX_MB] = {};
-  cudaStream_t mb_streams[MAX_MB] = {};
+  DevBuf host_wave[2], host_cond[2], host_tokens, host_tok16;  // m2m_transcribe_host device staging (double-buffered)
+  int16_t* pinned_tok = nullptr;                 // pinned host landing buffer of the int16 token read-back
+  size_t pinned_tok_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[2] = {};
+  int* h_done = nullptr;                         // pinned stop flag
+  cudaEvent_t poll_ev = nullptr;
   cudaStream_t own_stream = nullptr;
-  int persist_blocks_per_sm = 4;
-  int attn_stages = 3;  // operand-ring depth of decode_attn_kernel (M2M_ATTN_STAGES = 3 | 4)
-  bool lean_gemm = false;  // set while capturing micro-batched decode steps
-  bool pdl = false;        // set while launching a decode step with programmatic dependent launch
-  int n_microbatch = 1;  // >1: independent decode chains on separate streams (M2M_MICROBATCHES); measured gain ~1 %
 
-  std::vector<cudaGraphExec_t> step_graphs;  // one per micro-batch
+  cudaGraphExec_t step_graph = nullptr;
   GraphKey graph_key;
   size_t graph_nodes = 0;
 
+  // instrumented pass: one begin/end event pair per timed launch group, tagged (class | step << 8)
+  bool timing_on = false;
   std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_tag;
+  size_t ev_next = 0;
   m2m_stats stats;
 };
 
@@ -146,6 +166,56 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
     (ctx)->stats.kernel_launches++;                                                          \
   } while (0)
 
+// ------------------------------------------------------------------ instrumented pass (flag bit 1)
+// One begin/end CUDA-event pair around every timed launch group, on the launching stream; tag = class | step << 8.
+struct TimedScope {
+  m2m_ctx* c;
+  cudaStream_t s;
+  bool on;
+  TimedScope(m2m_ctx* c_, int cls, cudaStream_t s_, int step = 0) : c(c_), s(s_), on(c_->timing_on) {
+    if (!on) return;
+    while (c->ev_pool.size() < c->ev_next + 2) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+      c->ev_pool.push_back(e);
+    }
+    cudaEventRecord(c->ev_pool[c->ev_next], s);
+    c->ev_tag.push_back(cls | (step << 8));
+  }
+  ~TimedScope() {
+    if (!on) return;
+    cudaEventRecord(c->ev_pool[c->ev_next + 1], s);
+    c->ev_next += 2;
+  }
+};
+
+static void timing_begin(m2m_ctx* c) {
+  c->timing_on = (c->flags & 2u) != 0;
+  c->ev_next = 0;
+  c->ev_tag.clear();
+  if (c->timing_on) {
+    for (int i = 0; i < 16; ++i) {
+      c->stats.class_ms[i] = 0.0;
+      c->stats.class_launches[i] = 0;
+    }
+  }
+}
+
+// after a stream synchronize: sums the pair durations per class; decode pairs of steps >= executed_steps (no-op
+// launches after the stop condition) are ignored
+static void timing_collect(m2m_ctx* c, int executed_steps) {
+  if (!c->timing_on) return;
+  for (size_t i = 0; i < c->ev_tag.size(); ++i) {
+    const int cls = c->ev_tag[i] & 0xff, step = c->ev_tag[i] >> 8;
+    if (cls >= KC_DEC_SELF_ATTN && step >= executed_steps) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]) != cudaSuccess) continue;
+    c->stats.class_ms[cls] += ms;
+    c->stats.class_launches[cls] += 1;
+  }
+  c->timing_on = false;
+}
+
 // ------------------------------------------------------------------ GEMM dispatch
 // C = A[M,K] . W[N,K]^T with epilogue.  bf16 operands with large M go to the tcgen05 kernel,
 // everything else (fp32 parity mode, small M) to the CUDA-core kernel.
@@ -156,7 +226,7 @@ static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K
   cudaError_t e;
   if constexpr (std::is_same<T, bf16>::value) {
     if (!(c->flags & 8u) && tc::supported(M, N, K, lda)) {
-      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms, c->lean_gemm, c->pdl);
+      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms);
       if (e != cudaSuccess) {
         set_error("tcgen05 gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
         return M2M_ERR_CUDA;
@@ -174,31 +244,13 @@ static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K
   return 0;
 }
 
-// fused RMSNorm + GEMM on tcgen05 (bf16 contexts, decode step): A = bf16 residual stream, W = ln-folded weights
-template <typename Epi>
-static int gemm_rms(m2m_ctx* c, const bf16* xb, const bf16* W_ln, int M, int N, int K, Epi epi, const DecState* st,
-                    cudaStream_t s) {
-  if (M == 0) return 0;
-  cudaError_t e = tc::launch_rms(xb, K, W_ln, M, N, K, c->cfg.ln_eps, epi, st, s, c->num_sms, c->lean_gemm);
-  if (e != cudaSuccess) {
-    set_error("fused rmsnorm-gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
-    return M2M_ERR_CUDA;
-  }
-  c->stats.kernel_launches++;
-  return 0;
-}
-
 template <typename TO>
 static int rmsnorm(m2m_ctx* c, const float* x, const float* w, TO* y, size_t rows, const DecState* st, cudaStream_t s) {
   if (rows == 0) return 0;
   int D = c->cfg.d_model;
   unsigned blocks = (unsigned)((rows + 7) / 8);
-  cudaError_t le = launch_k(rmsnorm_kernel<TO>, dim3(blocks), dim3(256), 0, s, c->pdl, x, w, y, (int)rows, D, c->cfg.ln_eps, st);
-  if (le != cudaSuccess) {
-    set_error("rmsnorm launch failed: %s", cudaGetErrorString(le));
-    return M2M_ERR_CUDA;
-  }
-  c->stats.kernel_launches++;
+  rmsnorm_kernel<TO><<<blocks, 256, 0, s>>>(x, w, y, (int)rows, D, c->cfg.ln_eps, st);
+  LAUNCH_CHECK(c);
   return 0;
 }
 
@@ -208,7 +260,7 @@ static int seq_attn(m2m_ctx* c, const T* Q, int ldq, const T* K, const T* V, siz
   const int KT = Lk <= 256 ? Lk : 128;  // key tile staged in shared memory (single tile for the encoder)
   size_t smem = ((size_t)KT * (65 + 64) + 8 * (size_t)KT) * sizeof(float);
   auto kern = seq_attn_kernel<T, CAUSAL>;
-  M2M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (65 + 64 + 8) * 4));
+  M2M_CUDA(tc::ensure_smem_attr(reinterpret_cast<const void*>(kern), 256 * (65 + 64 + 8) * 4));
   dim3 grid((Lq + SEQ_ATTN_QT - 1) / SEQ_ATTN_QT, c->cfg.n_heads, B);
   kern<<<grid, 256, smem, s>>>(Q, ldq, K, V, kv_bs, kv_hs, kv_js, O, ldo, Lq, Lk, bias, bias_ld, bias_zero, KT);
   LAUNCH_CHECK(c);
@@ -244,14 +296,19 @@ static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_m
     EpiPower epi{c->mel_power.as<float>(), ldp, c->n_freq};
     cudaError_t e;
     if (use_tc) {
-      size_t total = rows * (size_t)(g.n_fft / 8);
-      unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16);
-      frame_split_kernel<<<blocks, 256, 0, s>>>(d_wave, c->window, c->mel_a3.as<bf16>(), S, T, g.hop, g.n_fft, (int)r0,
-                                                (int)rows, slab_rows * g.n_fft);
-      LAUNCH_CHECK(c);
+      {
+        TimedScope ts(c, KC_MEL_FRAME, s);
+        size_t total = rows * (size_t)(g.n_fft / 8);
+        unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16);
+        frame_split_kernel<<<blocks, 256, 0, s>>>(d_wave, c->window, c->mel_a3.as<bf16>(), S, T, g.hop, g.n_fft, (int)r0,
+                                                  (int)rows, slab_rows * g.n_fft);
+        LAUNCH_CHECK(c);
+      }
+      TimedScope ts(c, KC_MEL_DFT, s);
       e = tc::launch_cfg<128, 2, EpiPower, 3>(c->mel_a3.as<bf16>(), g.n_fft, c->dft_basis3, (int)rows, c->dft_rows,
                                               g.n_fft, epi, nullptr, s, (int)slab_rows, c->basis_split_rows);
     } else {
+      TimedScope ts(c, KC_MEL_DFT, s);
       FrameA a{d_wave, c->window, S, T, g.hop, g.n_fft / 2, (int)r0};
       e = launch_gemm_simt(a, c->dft_basis, g.n_fft, (int)rows, c->dft_rows, g.n_fft, epi, nullptr, s, c->num_sms);
     }
@@ -261,6 +318,7 @@ static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_m
     }
     c->stats.kernel_launches++;
     M2M_REQUIRE(g.d_model <= 512, "mel_band_log: n_mels %d > 512 is not supported", g.d_model);
+    TimedScope ts(c, KC_MEL_BAND, s);
     const unsigned bthreads = (unsigned)((g.d_model + 31) / 32 * 32);
     const unsigned bblocks = (unsigned)std::min<size_t>(rows, (size_t)c->num_sms * 5);
     mel_band_log_kernel<<<bblocks, bthreads, 2 * (size_t)ldp * sizeof(float), s>>>(
@@ -271,22 +329,31 @@ static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_m
   return 0;
 }
 
-static int condition_impl(m2m_ctx* c, const float* d_feature, const int64_t* d_cond, int B, int T, float* d_embeds,
-                          cudaStream_t s) {
-  if (B == 0) return 0;
-  const m2m_config& g = c->cfg;
-  M2M_TRY(c->dec_err.ensure(sizeof(int), nullptr));
-  M2M_CUDA(cudaMemsetAsync(c->dec_err.p, 0, sizeof(int), s));
-  size_t total = (size_t)B * (T + g.n_cond) * (g.d_model / 4);
-  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
-  condition_kernel<<<blocks, 256, 0, s>>>(d_feature, d_cond, c->cond_emb, c->cond_off, c->cond_rows, d_embeds, B, T,
-                                          g.d_model, g.n_cond, c->dec_err.as<int>());
-  LAUNCH_CHECK(c);
+// The out-of-range flag (nn.Embedding's IndexError in the reference) is left in dec_err; `check_now` reads it back
+// (one stream synchronize).  The fused generate path checks it after its own final synchronize instead.
+static int condition_check(m2m_ctx* c, cudaStream_t s) {
   int err = 0;
   M2M_CUDA(cudaMemcpyAsync(&err, c->dec_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   M2M_CUDA(cudaStreamSynchronize(s));
   M2M_REQUIRE(err == 0, "conditioning: cond_index out of range (IndexError in the reference's nn.Embedding)");
   return 0;
+}
+
+static int condition_impl(m2m_ctx* c, const float* d_feature, const int64_t* d_cond, int B, int T, float* d_embeds,
+                          bool check_now, cudaStream_t s) {
+  if (B == 0) return 0;
+  const m2m_config& g = c->cfg;
+  M2M_TRY(c->dec_err.ensure(sizeof(int), nullptr));
+  M2M_CUDA(cudaMemsetAsync(c->dec_err.p, 0, sizeof(int), s));
+  {
+    TimedScope ts(c, KC_COND, s);
+    size_t total = (size_t)B * (T + g.n_cond) * (g.d_model / 4);
+    unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    condition_kernel<<<blocks, 256, 0, s>>>(d_feature, d_cond, c->cond_emb, c->cond_off, c->cond_rows, d_embeds, B, T,
+                                            g.d_model, g.n_cond, c->dec_err.as<int>());
+    LAUNCH_CHECK(c);
+  }
+  return check_now ? condition_check(c, s) : 0;
 }
 
 // ------------------------------------------------------------------ encoder
@@ -309,48 +376,59 @@ static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d
   T* qkv = c->enc_qkv.as<T>();
   T* ao = c->enc_ao.as<T>();
   T* gg = c->enc_g.as<T>();
-  M2M_CUDA(cudaMemcpyAsync(x, d_embeds, M * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  {
+    TimedScope ts(c, KC_COND, s);
+    M2M_CUDA(cudaMemcpyAsync(x, d_embeds, M * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  auto norm = [&](const float* w, auto* out) -> int {
+    TimedScope ts(c, KC_ENC_NORM, s);
+    return rmsnorm(c, x, w, out, M, nullptr, s);
+  };
   for (int l = 0; l < g.n_layers; ++l) {
     const EncLayerW& w = c->enc[l];
-    M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, M, nullptr, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
-    bool attn_done = false;
-    if constexpr (std::is_same<T, bf16>::value) {
-      if (!(c->flags & 64u) && tc::enc_attn_supported(L, I, 3 * I)) {  // fused tcgen05 attention
-        cudaError_t e = tc::launch_enc_attn(qkv, 3 * I, B, L, g.n_heads, ao, I, c->enc_bias, c->enc_bias_ld,
-                                            g.max_enc_len - 1, s);
-        if (e != cudaSuccess) {
-          set_error("tcgen05 encoder attention launch failed: %s", cudaGetErrorString(e));
-          return M2M_ERR_CUDA;
-        }
-        c->stats.kernel_launches++;
-        attn_done = true;
-      }
+    M2M_TRY(norm(w.ln0, h));
+    {
+      TimedScope ts(c, KC_ENC_GEMM, s);
+      M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
     }
-    if constexpr (std::is_same<T, bf16>::value) {
-      if (!attn_done && !(c->flags & 64u)) {  // longer inputs (e.g. the 22.05 kHz training shape, L = 261): key-tiled kernel
-        cudaError_t e = tc::launch_seq_attn(qkv, 3 * I, B, L, g.n_heads, qkv, qkv, (uint64_t)M, 3 * I, I, 2 * I, 64, L, 0, L, ao,
-                                            I, c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, false, s);
-        if (e != cudaSuccess) {
-          set_error("tcgen05 tiled encoder attention launch failed: %s", cudaGetErrorString(e));
-          return M2M_ERR_CUDA;
+    {
+      TimedScope ts(c, KC_ENC_ATTN, s);
+      bool attn_done = false;
+      if constexpr (std::is_same<T, bf16>::value) {
+        if (!(c->flags & 64u)) {
+          cudaError_t e;
+          if (tc::enc_attn_supported(L, I, 3 * I))  // fused tcgen05 attention, all keys in one tile
+            e = tc::launch_enc_attn(qkv, 3 * I, B, L, g.n_heads, ao, I, c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s);
+          else  // longer inputs: key-tiled kernel
+            e = tc::launch_seq_attn(qkv, 3 * I, B, L, g.n_heads, qkv, qkv, (uint64_t)M, 3 * I, I, 2 * I, 64, L, 0, L, ao, I,
+                                    c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, false, s);
+          if (e != cudaSuccess) {
+            set_error("tcgen05 encoder attention launch failed: %s", cudaGetErrorString(e));
+            return M2M_ERR_CUDA;
+          }
+          c->stats.kernel_launches++;
+          attn_done = true;
         }
-        c->stats.kernel_launches++;
-        attn_done = true;
       }
+      if (!attn_done)
+        M2M_TRY((seq_attn<T, false>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)L * 3 * I, 64, 3 * I, ao, I, B, L, L,
+                                    c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s)));
     }
-    if (!attn_done)
-      M2M_TRY((seq_attn<T, false>(c, qkv, 3 * I, qkv + I, qkv + 2 * I, (size_t)L * 3 * I, 64, 3 * I, ao, I, B, L, L,
-                                  c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s)));
-    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
-    M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, M, nullptr, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));
-    M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, (int)M, D, F, EpiResidual{x, D}, nullptr, s));
+    {
+      TimedScope ts(c, KC_ENC_GEMM, s);
+      M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, (int)M, D, I, EpiResidual{x, D}, nullptr, s));
+    }
+    M2M_TRY(norm(w.ln1, h));
+    {
+      TimedScope ts(c, KC_ENC_GEMM, s);
+      M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, (int)M, 2 * F, D, EpiGatedGelu<T>{gg, F}, nullptr, s));
+      M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, (int)M, D, F, EpiResidual{x, D}, nullptr, s));
+    }
   }
-  if (d_out) M2M_TRY(rmsnorm<float>(c, x, c->enc_final_ln, d_out, M, nullptr, s));
+  if (d_out) M2M_TRY(norm(c->enc_final_ln, d_out));
   if (keep_typed) {
     M2M_TRY(c->enc_out.ensure(M * D * sizeof(T), &c->generation));
-    M2M_TRY(rmsnorm<T>(c, x, c->enc_final_ln, c->enc_out.as<T>(), M, nullptr, s));
+    M2M_TRY(norm(c->enc_final_ln, c->enc_out.as<T>()));
   }
   return 0;
 }
@@ -362,6 +440,7 @@ static int cross_kv_impl(m2m_ctx* c, const T* enc_out, int B, int L, cudaStream_
   const int D = g.d_model, I = g.n_heads * g.d_kv;
   const size_t M = (size_t)B * L;
   M2M_TRY(c->ckv.ensure((size_t)g.n_layers * M * 2 * I * sizeof(T), &c->generation));
+  TimedScope ts(c, KC_CROSS_KV, s);
   for (int l = 0; l < g.n_layers; ++l) {
     T* dst = c->ckv.as<T>() + (size_t)l * M * 2 * I;  // [K block: B*L*I | V block: B*L*I], each [b][h][j][64]
     M2M_TRY(gemm<T>(c, enc_out, D, (const T*)c->dec[l].wckv, (int)M, 2 * I, D,
@@ -371,159 +450,217 @@ static int cross_kv_impl(m2m_ctx* c, const T* enc_out, int B, int L, cudaStream_
 }
 
 // ------------------------------------------------------------------ one decode step (a8, a9)
-struct StepTiming {
-  bool on = false;
-  size_t next = 0;
+// bf16 contexts run the GEMM chain between the attention kernels as cluster-phased tcgen05 launches
+// (chain_tc.cuh): per step  K0 = QKV(layer 0);  per layer  self-attention, KB = [o-proj + residual | cross-q],
+// cross-attention, KA = [co-proj + residual | Wi + gated GELU | Wffo + residual | QKV(layer + 1) or lm_head].
+// 27 launches per step instead of 72.
+static bool use_chain(const m2m_ctx* c) {
+  const m2m_config& g = c->cfg;
+  return g.precision == M2M_BF16 && !(c->flags & 8u) && !(c->flags & 128u) && g.d_model == 64 * tc::CHAIN_CS &&
+         g.n_heads * g.d_kv == 512 && g.d_ff == 192 * tc::CHAIN_CS && g.vocab <= 80 * tc::CHAIN_CS && g.vocab % 16 == 0;
+}
+
+struct ChainPlan {
+  tc::ChainParams k0;
+  std::vector<tc::ChainParams> kb, ka;
 };
 
-// One decode step for the rows [r0, r0 + nb) of a batch of B rows ("micro-batch"): every per-row buffer is
-// addressed with the row offset, the micro-batch has its own DecState, so several micro-batches run as
-// independent chains on different streams (their latency-bound GEMMs overlap the HBM-bound attention of the
-// others).
+static int build_chain_plan(m2m_ctx* c, int B, int L, int max_length, float* logits, ChainPlan* plan) {
+  const m2m_config& g = c->cfg;
+  const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
+  const int Tmax = max_length;
+  const DecState* st = c->dec_state.as<DecState>();
+  float* x = c->dec_x.as<float>();
+  bf16* xb = c->dec_xb.as<bf16>();
+  bf16* q = c->dec_q.as<bf16>();
+  bf16* ao = c->dec_ao.as<bf16>();
+  bf16* gg = c->dec_g.as<bf16>();
+  float* ss = c->dec_ss.as<float>();
+  const size_t self_layer = (size_t)B * Tmax * I;
+  auto base = [&](tc::ChainParams& P, int n_phases) {
+    memset(&P, 0, sizeof(P));
+    P.n_phases = n_phases;
+    P.M = B;
+    P.eps = g.ln_eps;
+    P.inv_d = 1.f / (float)D;
+    P.ss = ss;
+    P.st = st;
+  };
+  auto residual = [&](tc::ChainPhase* ph, const bf16* A, int K, const void* W) {
+    bool ok = tc::chain_phase(ph, A, B, K, (const bf16*)W, D, 1, 64, D, tc::CH_RESIDUAL);
+    ph->out0 = x;
+    ph->out1 = xb;
+    ph->ld = D;
+    return ok;
+  };
+  auto qkv = [&](tc::ChainPhase* ph, int l) {
+    bool ok = tc::chain_phase(ph, xb, B, D, c->dec[l].wqkv_ln, 3 * I, 2, 128, 3 * I, tc::CH_QKV);
+    bf16* kc = c->skv.as<bf16>() + (size_t)(2 * l) * self_layer;
+    ph->out0 = q;
+    ph->out1 = kc;
+    ph->out2 = kc + self_layer;
+    ph->s0 = (long long)Tmax * 64;
+    ph->s1 = (long long)Tmax * I;
+    ph->inner = I;
+    return ok;
+  };
+  bool ok = true;
+  base(plan->k0, 1);
+  ok = ok && qkv(&plan->k0.ph[0], 0);
+  plan->kb.resize(g.n_layers);
+  plan->ka.resize(g.n_layers);
+  for (int l = 0; l < g.n_layers && ok; ++l) {
+    const DecLayerW& w = c->dec[l];
+    tc::ChainParams& kb = plan->kb[l];
+    base(kb, 2);
+    ok = ok && residual(&kb.ph[0], ao, I, w.wo);
+    ok = ok && tc::chain_phase(&kb.ph[1], xb, B, D, w.wcq_ln, 96 * tc::CHAIN_CS, 1, 96, I, tc::CH_STORE);
+    kb.ph[1].out0 = q;
+    kb.ph[1].ld = I;
+    tc::ChainParams& ka = plan->ka[l];
+    base(ka, 4);
+    ok = ok && residual(&ka.ph[0], ao, I, w.wco);
+    ok = ok && tc::chain_phase(&ka.ph[1], xb, B, D, w.wi_ln, 2 * F, 2, 192, 2 * F, tc::CH_GELU);
+    ka.ph[1].out0 = gg;
+    ka.ph[1].ld = F;
+    ok = ok && residual(&ka.ph[2], gg, F, w.wffo);
+    if (l + 1 < g.n_layers) {
+      ok = ok && qkv(&ka.ph[3], l + 1);
+    } else {
+      ok = ok && tc::chain_phase(&ka.ph[3], xb, B, D, c->lm_head_ln, V, 1, 80, V, tc::CH_LOGITS);
+      ka.ph[3].out0 = logits;
+      ka.ph[3].ld = V;
+    }
+  }
+  if (!ok) {
+    set_error("decode chain: tensor-map encoding failed");
+    return M2M_ERR_CUDA;
+  }
+  return 0;
+}
+
 template <typename T>
-static int decode_step_launch(m2m_ctx* c, int B, int r0, int nb, int mb, int L, int max_length, const int64_t* forced,
-                              float* logits_all, bool skip_finished, StepTiming* tm, cudaStream_t s,
-                              bool persist = false) {
+static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const int64_t* forced, float* logits_all,
+                              bool skip_finished, const ChainPlan* plan, int step, cudaStream_t s) {
   const m2m_config& g = c->cfg;
   const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
   const int Tmax = max_length;  // cache positions per row
-  DecState* st = c->dec_state.as<DecState>() + mb;
-  float* x = c->dec_x.as<float>() + (size_t)r0 * D;
-  T* h = c->dec_h.as<T>() + (size_t)r0 * D;
-  T* q = c->dec_q.as<T>() + (size_t)r0 * I;
-  T* ao = c->dec_ao.as<T>() + (size_t)r0 * I;
-  T* gg = c->dec_g.as<T>() + (size_t)r0 * F;
-  float* logits = c->dec_logits.as<float>() + (size_t)r0 * V;
-  uint8_t* fin = c->dec_finished.as<uint8_t>() + r0;
-  int64_t* tokens = c->dec_tokens.as<int64_t>() + (size_t)r0 * max_length;
-  if (forced) forced += (size_t)r0 * max_length;
-  if (logits_all) logits_all += (size_t)r0 * (max_length - 1) * V;
+  DecState* st = c->dec_state.as<DecState>();
+  float* x = c->dec_x.as<float>();
+  T* h = c->dec_h.as<T>();
+  T* q = c->dec_q.as<T>();
+  T* ao = c->dec_ao.as<T>();
+  T* gg = c->dec_g.as<T>();
+  float* logits = c->dec_logits.as<float>();
+  uint8_t* fin = c->dec_finished.as<uint8_t>();
+  int64_t* tokens = c->dec_tokens.as<int64_t>();
   const uint8_t* fin_skip = skip_finished ? fin : nullptr;
   const size_t self_layer = (size_t)B * Tmax * I;  // elements per K (or V) per layer
   const size_t cross_layer = (size_t)B * L * 2 * I;
   constexpr bool FAST = !std::is_same<T, float>::value;
-  dim3 agrid(g.n_heads, nb);
-  const unsigned pgrid = (unsigned)std::min<long>((long)c->num_sms * c->persist_blocks_per_sm, (long)nb * g.n_heads);
-  // programmatic dependent launch between the kernels of the step (bf16 / tcgen05 path only: every kernel launched
-  // with the attribute calls pdl_wait() before it touches upstream data)
-  struct PdlGuard {
-    m2m_ctx* c;
-    ~PdlGuard() { c->pdl = false; }
-  } pdl_guard{c};
-  c->pdl = std::is_same<T, bf16>::value && (c->flags & 4096u) && !(c->flags & 8u) && !persist && !(tm && tm->on);
-  // bf16 contexts on tcgen05: RMSNorm is fused into the consuming GEMM (no rmsnorm launches, no h buffer)
-  bool fuse = false;
-  bf16* xb = nullptr;
-  if constexpr (std::is_same<T, bf16>::value) {
-    fuse = !(c->flags & 8u) && (c->flags & 128u) && D % tc::BK == 0;  // opt-in: measured 2.4 % slower than the rmsnorm kernel
-    xb = c->dec_xb.as<bf16>() + (size_t)r0 * D;
-  }
+  dim3 agrid(g.n_heads, B);
   auto attn = [&](bool self, const T* kp, const T* vp) -> int {
-    if (self) {
-      if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
-      if (persist)
-        decode_attn_persist_kernel<T, true, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64,
-                                                                           0, c->dec_bias, g.max_positions, ao,
-                                                                           g.n_heads, nb, st, fin_skip);
-      else if (c->attn_stages == 4)
-        decode_attn_kernel<T, true, FAST, 4><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
-                                                                   c->dec_bias, g.max_positions, ao, g.n_heads, st,
-                                                                   fin_skip);
-      else
-        (void)launch_k(decode_attn_kernel<T, true, FAST, 3>, agrid, dim3(128), 0, s, c->pdl, (const T*)q, kp, vp,
-                       (size_t)Tmax * I, (size_t)Tmax * 64, 0, (const float*)c->dec_bias, g.max_positions, ao, g.n_heads,
-                       (const DecState*)st, fin_skip);
-      LAUNCH_CHECK(c);
-      if (tm && tm->on) cudaEventRecord(c->ev_pool[tm->next++], s);
-    } else {
-      if (persist)
-        decode_attn_persist_kernel<T, false, FAST, 4><<<pgrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L,
-                                                                            nullptr, 0, ao, g.n_heads, nb, st, fin_skip);
-      else if (c->attn_stages == 4)
-        decode_attn_kernel<T, false, FAST, 4><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr,
-                                                                    0, ao, g.n_heads, st, fin_skip);
-      else
-        (void)launch_k(decode_attn_kernel<T, false, FAST, 3>, agrid, dim3(128), 0, s, c->pdl, (const T*)q, kp, vp,
-                       (size_t)L * I, (size_t)L * 64, L, (const float*)nullptr, 0, ao, g.n_heads, (const DecState*)st,
-                       fin_skip);
-      LAUNCH_CHECK(c);
-    }
+    TimedScope ts(c, self ? KC_DEC_SELF_ATTN : KC_DEC_CROSS_ATTN, s, step);
+    if (self)
+      decode_attn_kernel<T, true, FAST, 3><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
+                                                                 c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
+    else
+      decode_attn_kernel<T, false, FAST, 3><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr, 0,
+                                                                  ao, g.n_heads, st, fin_skip);
+    LAUNCH_CHECK(c);
     return 0;
   };
+  auto chain = [&](const tc::ChainParams& P) -> int {
+    TimedScope ts(c, KC_DEC_CHAIN, s, step);
+    cudaError_t e = tc::launch_chain(P, s);
+    if (e != cudaSuccess) {
+      set_error("decode chain launch failed: %s", cudaGetErrorString(e));
+      return M2M_ERR_CUDA;
+    }
+    c->stats.kernel_launches++;
+    return 0;
+  };
+  bf16* xb = nullptr;
+  float* ss = nullptr;
+  if (plan != nullptr) {
+    xb = c->dec_xb.as<bf16>();
+    ss = c->dec_ss.as<float>();
+    M2M_TRY(chain(plan->k0));
+  }
   for (int l = 0; l < g.n_layers; ++l) {
     const DecLayerW& w = c->dec[l];
-    T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer + (size_t)r0 * Tmax * I;
+    T* kc = c->skv.as<T>() + (size_t)(2 * l) * self_layer;
     T* vc = kc + self_layer;
-    const T* ck = c->ckv.as<T>() + (size_t)l * cross_layer + (size_t)r0 * L * I;
+    const T* ck = c->ckv.as<T>() + (size_t)l * cross_layer;
     const T* cv = ck + (size_t)B * L * I;
+    if (plan != nullptr) {
+      M2M_TRY(attn(true, kc, vc));
+      M2M_TRY(chain(plan->kb[l]));
+      M2M_TRY(attn(false, ck, cv));
+      M2M_TRY(chain(plan->ka[l]));
+      continue;
+    }
     const EpiQKVCache<T> epi_qkv{q, kc, vc, I, (size_t)Tmax * 64, (size_t)Tmax * I};
-    if constexpr (std::is_same<T, bf16>::value) {
-      if (fuse) {
-        M2M_TRY(gemm_rms(c, xb, w.wqkv_ln, nb, 3 * I, D, epi_qkv, st, s));
-        M2M_TRY(attn(true, kc, vc));
-        M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, nb, D, I, EpiResidualDual{x, xb, D}, st, s));
-        M2M_TRY(gemm_rms(c, xb, w.wcq_ln, nb, I, D, EpiStore<T>{q, I}, st, s));
-        M2M_TRY(attn(false, ck, cv));
-        M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, nb, D, I, EpiResidualDual{x, xb, D}, st, s));
-        M2M_TRY(gemm_rms(c, xb, w.wi_ln, nb, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
-        M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, nb, D, F, EpiResidualDual{x, xb, D}, st, s));
-        continue;
-      }
+    {
+      TimedScope ts(c, KC_DEC_CHAIN, s, step);
+      M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, B, st, s));
+      M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, B, 3 * I, D, epi_qkv, st, s));
     }
-    M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, nb, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, nb, 3 * I, D, epi_qkv, st, s));
     M2M_TRY(attn(true, kc, vc));
-    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, nb, D, I, EpiResidual{x, D}, st, s));
-    M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, nb, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, nb, I, D, EpiStore<T>{q, I}, st, s));
+    {
+      TimedScope ts(c, KC_DEC_CHAIN, s, step);
+      M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wo, B, D, I, EpiResidual{x, D}, st, s));
+      M2M_TRY(rmsnorm<T>(c, x, w.ln1, h, B, st, s));
+      M2M_TRY(gemm<T>(c, h, D, (const T*)w.wcq, B, I, D, EpiStore<T>{q, I}, st, s));
+    }
     M2M_TRY(attn(false, ck, cv));
-    M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, nb, D, I, EpiResidual{x, D}, st, s));
-    M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, nb, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, nb, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
-    M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, nb, D, F, EpiResidual{x, D}, st, s));
-  }
-  bool head_done = false;
-  if constexpr (std::is_same<T, bf16>::value) {
-    if (fuse) {
-      M2M_TRY(gemm_rms(c, xb, c->lm_head_ln, nb, V, D, EpiStore<float>{logits, V}, st, s));
-      head_done = true;
+    {
+      TimedScope ts(c, KC_DEC_CHAIN, s, step);
+      M2M_TRY(gemm<T>(c, ao, I, (const T*)w.wco, B, D, I, EpiResidual{x, D}, st, s));
+      M2M_TRY(rmsnorm<T>(c, x, w.ln2, h, B, st, s));
+      M2M_TRY(gemm<T>(c, h, D, (const T*)w.wi, B, 2 * F, D, EpiGatedGelu<T>{gg, F}, st, s));
+      M2M_TRY(gemm<T>(c, gg, F, (const T*)w.wffo, B, D, F, EpiResidual{x, D}, st, s));
     }
   }
-  if (!head_done) {
-    M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, nb, st, s));
-    M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, nb, V, D, EpiStore<float>{logits, V}, st, s));
+  if (plan == nullptr) {
+    TimedScope ts(c, KC_DEC_CHAIN, s, step);
+    M2M_TRY(rmsnorm<T>(c, x, c->dec_final_ln, h, B, st, s));
+    M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, B, V, D, EpiStore<float>{logits, V}, st, s));
   }
-  (void)launch_k(select_token_kernel, dim3(nb), dim3(128), 0, s, c->pdl, (const float*)logits, V, tokens, max_length, forced,
-                 fin, (const float*)c->shared, x, D, logits_all, st, g.pad_id, g.eos_id, xb);
+  TimedScope ts(c, KC_DEC_SELECT, s, step);
+  select_token_kernel<<<B, 128, 0, s>>>(logits, V, tokens, max_length, forced, fin, c->shared, x, D, logits_all, st,
+                                        g.pad_id, g.eos_id, xb, ss, ss ? tc::CHAIN_CS : 0);
   LAUNCH_CHECK(c);
-  (void)launch_k(step_advance_kernel, dim3(1), dim3(1), 0, s, c->pdl, st, forced == nullptr ? 1 : 0);
+  step_advance_kernel<<<1, 1, 0, s>>>(st, forced == nullptr ? 1 : 0);
   LAUNCH_CHECK(c);
   return 0;
 }
 
 __global__ void decode_init_kernel(int64_t* tokens, int ld, uint8_t* finished, float* x, const float* table, int D,
-                                   int B, int bos, DecState* st, int n_states, int max_length, bf16* xb) {
+                                   int B, int bos, DecState* st, int max_length, bf16* xb, float* ss, int ss_ld) {
   int b = blockIdx.x;
   if (threadIdx.x == 0) {
     tokens[(size_t)b * ld] = bos;
     finished[b] = 0;
-    if (b < n_states) {
-      st[b].t = 0;
-      st[b].done = max_length <= 1 ? 1 : 0;
-      st[b].final_len = max_length <= 1 ? 1 : max_length;
-      st[b].unfinished = 0;
-      st[b].max_length = max_length;
+    if (b == 0) {
+      st->t = 0;
+      st->done = max_length <= 1 ? 1 : 0;
+      st->final_len = max_length <= 1 ? 1 : max_length;
+      st->unfinished = 0;
+      st->max_length = max_length;
     }
   }
-  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(table + (size_t)bos * D)[i];
-    reinterpret_cast<float4*>(x + (size_t)b * D)[i] = v;
-    if (xb != nullptr) {
-      const float o[4] = {v.x, v.y, v.z, v.w};
-      store4(xb + (size_t)b * D + 4 * i, o);
-    }
-  }
+  embed_row(table + (size_t)bos * D, x + (size_t)b * D, xb ? xb + (size_t)b * D : nullptr, ss ? ss + (size_t)b * ss_ld : nullptr,
+            ss_ld, D);
 }
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
 
 template <typename T>
 static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, int L, int max_length,
@@ -536,7 +673,6 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   if (out_len) *out_len = 1;
   if (B == 0) return 0;
   const int D = g.d_model, I = g.n_heads * g.d_kv, F = g.d_ff, V = g.vocab;
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
   M2M_TRY(encode_impl<T>(c, d_embeds, B, L, nullptr, true, s));
   M2M_TRY(cross_kv_impl<T>(c, c->enc_out.as<T>(), B, L, s));
@@ -544,6 +680,7 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   M2M_TRY(c->skv.ensure((size_t)g.n_layers * 2 * B * max_length * I * sizeof(T), &c->generation));
   M2M_TRY(c->dec_x.ensure((size_t)B * D * sizeof(float), &c->generation));
   M2M_TRY(c->dec_xb.ensure((size_t)B * D * sizeof(bf16), &c->generation));
+  M2M_TRY(c->dec_ss.ensure((size_t)B * tc::CHAIN_CS * sizeof(float), &c->generation));
   M2M_TRY(c->dec_h.ensure((size_t)B * D * sizeof(T), &c->generation));
   M2M_TRY(c->dec_q.ensure((size_t)B * I * sizeof(T), &c->generation));
   M2M_TRY(c->dec_ao.ensure((size_t)B * I * sizeof(T), &c->generation));
@@ -551,160 +688,113 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   M2M_TRY(c->dec_logits.ensure((size_t)B * V * sizeof(float), &c->generation));
   M2M_TRY(c->dec_finished.ensure((size_t)B, &c->generation));
   M2M_TRY(c->dec_tokens.ensure((size_t)B * max_length * sizeof(int64_t), &c->generation));
-  M2M_TRY(c->dec_state.ensure(MAX_MB * sizeof(DecState), &c->generation));
+  M2M_TRY(c->dec_state.ensure(sizeof(DecState), &c->generation));
 
   const int n_steps = max_length - 1;
-  const bool timing = (c->flags & 2u) != 0;
+  const bool timing = c->timing_on;
   const bool plain = d_forced == nullptr && d_logits == nullptr;
   const bool use_graph = (c->flags & 1u) && plain && !timing;
-  const bool skip_finished = (c->flags & 4u) && plain;
-  // micro-batches: independent decode chains on their own streams (only for the plain, graph-replayed path)
-  int nmb = 1;
-  const int want_mb = ((c->flags >> 8) & 0xF) ? (int)((c->flags >> 8) & 0xF) : c->n_microbatch;
-  if (use_graph && B >= 2 * 128) nmb = std::min<int>(want_mb, std::min(MAX_MB, B / 128));
-  if (nmb < 1) nmb = 1;
-  int mb_r0[MAX_MB + 1];
-  for (int i = 0; i <= nmb; ++i) mb_r0[i] = (int)((int64_t)B * i / nmb);
+  // the instrumented pass reads every row (the roofline counts B rows per launch)
+  const bool skip_finished = (c->flags & 4u) && plain && !timing;
+  const bool chain_mode = std::is_same<T, bf16>::value && use_chain(c);
+  ChainPlan plan;
+  if (chain_mode) M2M_TRY(build_chain_plan(c, B, L, max_length, c->dec_logits.as<float>(), &plan));
 
   int64_t* tokens = c->dec_tokens.as<int64_t>();
   M2M_CUDA(cudaMemsetAsync(tokens, 0, (size_t)B * max_length * sizeof(int64_t), s));  // pad_id == 0 rows
-  decode_init_kernel<<<B, 128, 0, s>>>(tokens, max_length, c->dec_finished.as<uint8_t>(),
-                                                       c->dec_x.as<float>(), c->shared, D, B, g.bos_id,
-                                                       c->dec_state.as<DecState>(), nmb, max_length,
-                                                       std::is_same<T, bf16>::value ? c->dec_xb.as<bf16>() : nullptr);
+  decode_init_kernel<<<B, 128, 0, s>>>(tokens, max_length, c->dec_finished.as<uint8_t>(), c->dec_x.as<float>(), c->shared,
+                                       D, B, g.bos_id, c->dec_state.as<DecState>(), max_length,
+                                       chain_mode ? c->dec_xb.as<bf16>() : nullptr,
+                                       chain_mode ? c->dec_ss.as<float>() : nullptr, tc::CHAIN_CS);
   LAUNCH_CHECK(c);
 
-  StepTiming tm;
-  if (timing) {
-    size_t need = (size_t)n_steps * g.n_layers * 2;
-    while (c->ev_pool.size() < need) {
-      cudaEvent_t e;
-      M2M_CUDA(cudaEventCreate(&e));
-      c->ev_pool.push_back(e);
-    }
-    tm.on = true;
-  }
-
   if (use_graph && n_steps > 0) {
-    bool hit = !c->step_graphs.empty() && (int)c->step_graphs.size() == nmb && c->graph_key.B == B &&
-               c->graph_key.L == L && c->graph_key.max_length == max_length &&
-               c->graph_key.generation == c->generation && c->graph_key.flags == c->flags;
+    bool hit = c->step_graph != nullptr && c->graph_key.B == B && c->graph_key.L == L &&
+               c->graph_key.max_length == max_length && c->graph_key.generation == c->generation &&
+               c->graph_key.flags == c->flags;
     if (!hit) {
-      for (auto ge : c->step_graphs) cudaGraphExecDestroy(ge);
-      c->step_graphs.clear();
-      for (int i = 0; i < nmb; ++i) {
-        cudaGraph_t graph = nullptr;
-        int64_t launches_before = c->stats.kernel_launches;
-        // capture on the context's own stream (the caller's may be the legacy default stream, which cannot be
-        // captured); the instantiated graphs are launched on the micro-batch streams.
-        cudaStream_t cs = c->own_stream;
-        M2M_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        c->lean_gemm = nmb > 1;
-        int rc = decode_step_launch<T>(c, B, mb_r0[i], mb_r0[i + 1] - mb_r0[i], i, L, max_length, nullptr, nullptr,
-                                       skip_finished, nullptr, cs, nmb > 1);
-        c->lean_gemm = false;
-        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-        c->graph_nodes = (size_t)(c->stats.kernel_launches - launches_before);
-        c->stats.kernel_launches = launches_before;
-        if (rc != 0) {
-          if (graph) cudaGraphDestroy(graph);
-          return rc;
-        }
-        if (ce != cudaSuccess) {
-          set_error("decode-step graph capture failed: %s", cudaGetErrorString(ce));
-          return M2M_ERR_CUDA;
-        }
-        cudaGraphExec_t ge = nullptr;
-        M2M_CUDA(cudaGraphInstantiate(&ge, graph, 0));
-        cudaGraphDestroy(graph);
-        c->step_graphs.push_back(ge);
+      if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+      c->step_graph = nullptr;
+      cudaGraph_t graph = nullptr;
+      int64_t launches_before = c->stats.kernel_launches;
+      // capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
+      cudaStream_t cs = c->own_stream;
+      M2M_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      int rc = decode_step_launch<T>(c, B, L, max_length, nullptr, nullptr, skip_finished, chain_mode ? &plan : nullptr, 0, cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      c->graph_nodes = (size_t)(c->stats.kernel_launches - launches_before);
+      c->stats.kernel_launches = launches_before;
+      if (rc != 0) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess) {
+        set_error("decode-step graph capture failed: %s", cudaGetErrorString(ce));
+        return M2M_ERR_CUDA;
+      }
+      cudaError_t ie = cudaGraphInstantiate(&c->step_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        c->step_graph = nullptr;
+        set_error("decode-step graph instantiation failed: %s", cudaGetErrorString(ie));
+        return M2M_ERR_CUDA;
       }
       c->graph_key.B = B; c->graph_key.L = L; c->graph_key.max_length = max_length;
       c->graph_key.generation = c->generation; c->graph_key.flags = c->flags;
     }
   }
 
-  M2M_CUDA(cudaEventCreate(&ev_begin));
-  M2M_CUDA(cudaEventCreate(&ev_end));
-  M2M_CUDA(cudaEventRecord(ev_begin, s));
-  // micro-batch i > 0 runs on its own stream, forked from and joined back into the caller's stream
-  cudaStream_t mbs[MAX_MB];
-  for (int i = 0; i < nmb; ++i) mbs[i] = (nmb == 1) ? s : c->mb_streams[i];
-  if (nmb > 1)
-    for (int i = 0; i < nmb; ++i) M2M_CUDA(cudaStreamWaitEvent(mbs[i], ev_begin, 0));
-  bool pending[MAX_MB] = {false}, stopped[MAX_MB] = {false};
-  for (int i = 0; i < nmb; ++i) c->h_done[i] = 0;
+  EventPair ev;
+  M2M_CUDA(cudaEventCreate(&ev.a));
+  M2M_CUDA(cudaEventCreate(&ev.b));
+  M2M_CUDA(cudaEventRecord(ev.a, s));
+  bool pending = false;
+  *c->h_done = 0;
   for (int step = 0; step < n_steps; ++step) {
-    bool all_stopped = true;
-    for (int i = 0; i < nmb; ++i) {
-      if (stopped[i]) continue;
-      all_stopped = false;
-      if (use_graph) {
-        M2M_CUDA(cudaGraphLaunch(c->step_graphs[i], mbs[i]));
-        c->stats.kernel_launches += (int64_t)c->graph_nodes;
-      } else {
-        M2M_TRY(decode_step_launch<T>(c, B, 0, B, 0, L, max_length, d_forced, d_logits, skip_finished, &tm, s));
+    if (use_graph) {
+      M2M_CUDA(cudaGraphLaunch(c->step_graph, s));
+      c->stats.kernel_launches += (int64_t)c->graph_nodes;
+    } else {
+      M2M_TRY(decode_step_launch<T>(c, B, L, max_length, d_forced, d_logits, skip_finished, chain_mode ? &plan : nullptr,
+                                    step, s));
+    }
+    // lagging, non-blocking stop detection: the device sets st->done; later launches are no-ops
+    if (d_forced == nullptr && (step & 15) == 15) {
+      if (pending && cudaEventQuery(c->poll_ev) == cudaSuccess) {
+        pending = false;
+        if (*c->h_done) break;
       }
-      // lagging, non-blocking stop detection: the device sets st->done; later launches are no-ops
-      if (d_forced == nullptr && (step & 15) == 15) {
-        if (pending[i] && cudaEventQuery(c->poll_ev[i]) == cudaSuccess) {
-          pending[i] = false;
-          if (c->h_done[i]) stopped[i] = true;
-        }
-        if (!pending[i] && !stopped[i]) {
-          M2M_CUDA(cudaMemcpyAsync(&c->h_done[i], &(c->dec_state.as<DecState>() + i)->done, sizeof(int),
-                                   cudaMemcpyDeviceToHost, mbs[i]));
-          M2M_CUDA(cudaEventRecord(c->poll_ev[i], mbs[i]));
-          pending[i] = true;
-        }
+      if (!pending) {
+        M2M_CUDA(cudaMemcpyAsync(c->h_done, &c->dec_state.as<DecState>()->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        M2M_CUDA(cudaEventRecord(c->poll_ev, s));
+        pending = true;
       }
     }
-    if (all_stopped) break;
   }
-  if (nmb > 1)
-    for (int i = 0; i < nmb; ++i) {
-      M2M_CUDA(cudaEventRecord(c->join_ev[i], mbs[i]));
-      M2M_CUDA(cudaStreamWaitEvent(s, c->join_ev[i], 0));
-    }
-  M2M_CUDA(cudaEventRecord(ev_end, s));
-  DecState hsts[MAX_MB];
-  M2M_CUDA(cudaMemcpyAsync(hsts, c->dec_state.p, nmb * sizeof(DecState), cudaMemcpyDeviceToHost, s));
+  M2M_CUDA(cudaEventRecord(ev.b, s));
+  DecState hst;
+  M2M_CUDA(cudaMemcpyAsync(&hst, c->dec_state.p, sizeof(DecState), cudaMemcpyDeviceToHost, s));
   if (d_tokens)
     M2M_CUDA(cudaMemcpyAsync(d_tokens, tokens, (size_t)B * max_length * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
   M2M_CUDA(cudaStreamSynchronize(s));
-  DecState hst = hsts[0];
-  for (int i = 0; i < nmb; ++i) {
-    if (n_steps > 0 && !hsts[i].done) {
-      set_error("internal: decode loop ended without reaching a stop condition (micro-batch %d, t=%d)", i, hsts[i].t);
-      return M2M_ERR_STATE;
-    }
-    // HF stops when ALL rows are finished: the batch length is the longest micro-batch
-    if (hsts[i].final_len > hst.final_len) hst.final_len = hsts[i].final_len;
-    if (hsts[i].t > hst.t) hst.t = hsts[i].t;
+  if (n_steps > 0 && !hst.done) {
+    set_error("internal: decode loop ended without reaching a stop condition (t=%d)", hst.t);
+    return M2M_ERR_STATE;
   }
   if (out_len) *out_len = hst.final_len;
   c->stats.decode_steps += hst.t;
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, ev_begin, ev_end);
+  cudaEventElapsedTime(&ms, ev.a, ev.b);
   c->stats.last_generate_ms = ms;
-  cudaEventDestroy(ev_begin);
-  cudaEventDestroy(ev_end);
   if (timing) {
-    double tot = 0;
-    int64_t bytes = 0;
-    size_t pairs = tm.next / 2;
-    int executed = hst.t;  // steps that actually did work
-    for (size_t i = 0; i < pairs; ++i) {
-      int step = (int)(i / g.n_layers);
-      if (step >= executed) break;
-      float e = 0.f;
-      cudaEventElapsedTime(&e, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]);
-      tot += e;
-      bytes += (int64_t)B * (step + 1) * 2 * I * (int64_t)sizeof(T);
-      c->stats.last_attn_launches = (int64_t)i + 1;
-    }
-    c->stats.last_attn_ms = tot;
-    c->stats.attn_bytes = bytes;
+    timing_collect(c, hst.t);
+    // algorithmic KV bytes of the executed launches: every row reads its whole cache (finished rows included)
+    int64_t self_bytes = 0;
+    for (int step = 0; step < hst.t; ++step) self_bytes += (int64_t)B * (step + 1) * 2 * I * (int64_t)sizeof(T) * g.n_layers;
+    c->stats.attn_bytes = self_bytes;
+    c->stats.cross_attn_bytes = (int64_t)hst.t * g.n_layers * B * L * 2 * I * (int64_t)sizeof(T);
+    c->stats.last_attn_ms = c->stats.class_ms[KC_DEC_SELF_ATTN];
+    c->stats.last_attn_launches = c->stats.class_launches[KC_DEC_SELF_ATTN];
   }
   return 0;
 }
@@ -716,14 +806,15 @@ static int generate_impl(m2m_ctx* c, const float* d_wave, const int64_t* d_cond,
   if (out_len) *out_len = 1;
   if (B == 0) return 0;
   const int T_ = 1 + S / g.hop, L = T_ + g.n_cond;
-  // mel is written straight behind the conditioning rows? No: rows interleave per batch, so stage it.
   DevBuf& mel = c->tf_x;  // reuse: [B, T, D] fp32
   M2M_TRY(mel.ensure((size_t)B * T_ * g.d_model * sizeof(float), &c->generation));
   M2M_TRY(c->embeds.ensure((size_t)B * L * g.d_model * sizeof(float), &c->generation));
   M2M_TRY(logmel_impl(c, d_wave, B, S, mel.as<float>(), s));
-  M2M_TRY(condition_impl(c, mel.as<float>(), d_cond, B, T_, c->embeds.as<float>(), s));
-  return generate_from_embeds_impl<T>(c, c->embeds.as<float>(), B, L, max_length, nullptr, d_tokens, nullptr, out_len, s);
+  M2M_TRY(condition_impl(c, mel.as<float>(), d_cond, B, T_, c->embeds.as<float>(), false, s));
+  M2M_TRY(generate_from_embeds_impl<T>(c, c->embeds.as<float>(), B, L, max_length, nullptr, d_tokens, nullptr, out_len, s));
+  return condition_check(c, s);  // the stream is idle by now: one 4-byte read-back
 }
+
 
 // ------------------------------------------------------------------ teacher-forced decoder (a10)
 template <typename T>
@@ -959,16 +1050,13 @@ int m2m_ctx_create(const m2m_config* cfg, int device, m2m_ctx** out) {
   c->device = device;
   c->num_sms = p.multiProcessorCount;
   memset(&c->stats, 0, sizeof(c->stats));
-  bool ok = cudaMallocHost((void**)&c->h_done, MAX_MB * sizeof(int)) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
-  for (int i = 0; i < MAX_MB && ok; ++i)
-    ok = cudaEventCreateWithFlags(&c->poll_ev[i], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming) == cudaSuccess &&
-         cudaStreamCreateWithFlags(&c->mb_streams[i], cudaStreamNonBlocking) == cudaSuccess;
-  if (const char* e = getenv("M2M_MICROBATCHES")) c->n_microbatch = std::max(1, std::min(MAX_MB, atoi(e)));
+  bool ok = cudaMallocHost((void**)&c->h_done, sizeof(int)) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->poll_ev, cudaEventDisableTiming) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->copy_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->copy_ev[1], cudaEventDisableTiming) == cudaSuccess;
   if (const char* e = getenv("M2M_FLAGS")) c->flags = (uint32_t)strtoul(e, nullptr, 0);  // A/B experiments
-  if (const char* e = getenv("M2M_ATTN_STAGES")) c->attn_stages = atoi(e) == 4 ? 4 : 3;
-  if (const char* e = getenv("M2M_PERSIST_BLOCKS")) c->persist_blocks_per_sm = std::max(1, std::min(8, atoi(e)));
   if (!ok) {
     set_error("context resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
@@ -982,19 +1070,20 @@ int m2m_ctx_destroy(m2m_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto ge : c->step_graphs) cudaGraphExecDestroy(ge);
+  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
                     &c->enc_out, &c->ckv, &c->skv, &c->dec_xb, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
-                    &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->tf_x, &c->tf_h,
-                    &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave, &c->host_cond, &c->host_tokens};
+                    &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->dec_ss, &c->tf_x, &c->tf_h,
+                    &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave[0], &c->host_wave[1], &c->host_cond[0],
+                    &c->host_cond[1], &c->host_tokens, &c->host_tok16};
   for (DevBuf* b : bufs) b->release();
   if (c->h_done) cudaFreeHost(c->h_done);
-  for (int i = 0; i < MAX_MB; ++i) {
-    if (c->poll_ev[i]) cudaEventDestroy(c->poll_ev[i]);
-    if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
-    if (c->mb_streams[i]) cudaStreamDestroy(c->mb_streams[i]);
-  }
+  if (c->poll_ev) cudaEventDestroy(c->poll_ev);
+  for (int k = 0; k < 2; ++k)
+    if (c->copy_ev[k]) cudaEventDestroy(c->copy_ev[k]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->pinned_tok) cudaFreeHost(c->pinned_tok);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return 0;
@@ -1115,7 +1204,9 @@ int m2m_finalize_weights(m2m_ctx* c) {
       const std::vector<float>* wq = nullptr;
       M2M_TRY(get_staged(c, key, (size_t)I * D, &wq));
       snprintf(key, sizeof(key), "transformer.decoder.block.%d.layer.1.layer_norm.weight", l);
-      M2M_TRY(fold_ln(*wq, std::string(key).c_str(), &dof[l].wcq_ln));
+      std::vector<float> wq_pad(*wq);
+      wq_pad.resize((size_t)std::max(I, 96 * tc::CHAIN_CS) * D, 0.f);  // zero rows up to 6 x 96 (chain_tc.cuh slices)
+      M2M_TRY(fold_ln(wq_pad, std::string(key).c_str(), &dof[l].wcq_ln));
     }
     M2M_TRY(stack_rows("transformer.decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, {"k", "v"}, I, D, tmp));
     dof[l].wckv = ab.push_typed(tmp, bf);
@@ -1306,7 +1397,7 @@ int m2m_logmel(m2m_ctx* c, const float* d_wave, int B, int S, float* d_mel, void
 
 int m2m_condition(m2m_ctx* c, const float* d_feature, const int64_t* d_cond, int B, int T, float* d_embeds, void* stream) {
   M2M_ENTER(c);
-  return condition_impl(c, d_feature, d_cond, B, T, d_embeds, s);
+  return condition_impl(c, d_feature, d_cond, B, T, d_embeds, true, s);
 }
 
 int m2m_encode(m2m_ctx* c, const float* d_embeds, int B, int L, float* d_out, void* stream) {
@@ -1320,6 +1411,7 @@ int m2m_generate_from_embeds(m2m_ctx* c, const float* d_embeds, int B, int L, in
                              int64_t* d_tokens, float* d_logits, int* out_len, void* stream) {
   M2M_ENTER(c);
   M2M_NEED_MODEL(c);
+  timing_begin(c);
   return c->cfg.precision == M2M_BF16
              ? generate_from_embeds_impl<bf16>(c, d_embeds, B, L, max_length, d_forced, d_tokens, d_logits, out_len, s)
              : generate_from_embeds_impl<float>(c, d_embeds, B, L, max_length, d_forced, d_tokens, d_logits, out_len, s);
@@ -1329,6 +1421,7 @@ int m2m_generate(m2m_ctx* c, const float* d_wave, const int64_t* d_cond, int B, 
                  int* out_len, void* stream) {
   M2M_ENTER(c);
   M2M_NEED_MODEL(c);
+  timing_begin(c);
   return c->cfg.precision == M2M_BF16 ? generate_impl<bf16>(c, d_wave, d_cond, B, S, max_length, d_tokens, out_len, s)
                                       : generate_impl<float>(c, d_wave, d_cond, B, S, max_length, d_tokens, out_len, s);
 }
@@ -1346,30 +1439,66 @@ int m2m_transcribe_host(m2m_ctx* c, const float* h_wave, int64_t n_seg, int S, c
   void* stream = c ? (void*)c->own_stream : nullptr;
   M2M_ENTER(c);
   M2M_NEED_MODEL(c);
-  M2M_REQUIRE(n_seg >= 0 && device_batch > 0 && h_wave && h_tokens, "m2m_transcribe_host: bad argument");
-  const int nc = c->cfg.n_cond;
-  for (int64_t i0 = 0; i0 < n_seg; i0 += device_batch) {
-    int nb = (int)std::min<int64_t>(device_batch, n_seg - i0);
-    M2M_TRY(c->host_wave.ensure((size_t)nb * S * sizeof(float), &c->generation));
-    M2M_TRY(c->host_cond.ensure((size_t)nb * std::max(1, nc) * sizeof(int64_t), &c->generation));
-    M2M_TRY(c->host_tokens.ensure((size_t)nb * max_length * sizeof(int64_t), &c->generation));
-    M2M_CUDA(cudaMemcpyAsync(c->host_wave.p, h_wave + (size_t)i0 * S, (size_t)nb * S * sizeof(float),
-                             cudaMemcpyHostToDevice, s));
+  M2M_REQUIRE(n_seg >= 0 && device_batch > 0 && h_wave && h_tokens && S > 0 && max_length >= 1,
+              "m2m_transcribe_host: bad argument");
+  const int nc = c->cfg.n_cond, ncp = std::max(1, nc);
+  const int64_t n_chunks = (n_seg + device_batch - 1) / device_batch;
+  if (n_chunks == 0) return 0;
+  const size_t cap = (size_t)std::min<int64_t>(device_batch, n_seg);
+  // double-buffered waveform staging: the upload of device batch i+1 (copy stream) overlaps the compute of batch i
+  for (int k = 0; k < 2; ++k) {
+    if (k == 1 && n_chunks == 1) break;
+    M2M_TRY(c->host_wave[k].ensure(cap * S * sizeof(float), &c->generation));
+    M2M_TRY(c->host_cond[k].ensure(cap * ncp * sizeof(int64_t), &c->generation));
+  }
+  M2M_TRY(c->host_tokens.ensure(cap * max_length * sizeof(int64_t), &c->generation));
+  M2M_TRY(c->host_tok16.ensure(cap * max_length * sizeof(int16_t), &c->generation));
+  if (c->pinned_tok_cap < cap * max_length) {  // pinned landing buffer of the int16 token read-back
+    if (c->pinned_tok) cudaFreeHost(c->pinned_tok);
+    c->pinned_tok = nullptr;
+    c->pinned_tok_cap = 0;
+    M2M_CUDA(cudaMallocHost((void**)&c->pinned_tok, cap * max_length * sizeof(int16_t)));
+    c->pinned_tok_cap = cap * max_length;
+  }
+  auto upload = [&](int64_t chunk) -> int {
+    const int k = (int)(chunk & 1);
+    const int64_t i0 = chunk * device_batch;
+    const size_t nb = (size_t)std::min<int64_t>(device_batch, n_seg - i0);
+    cudaStream_t cs = c->copy_stream;
+    M2M_CUDA(cudaMemcpyAsync(c->host_wave[k].p, h_wave + (size_t)i0 * S, nb * S * sizeof(float), cudaMemcpyHostToDevice, cs));
     if (h_cond)
-      M2M_CUDA(cudaMemcpyAsync(c->host_cond.p, h_cond + (size_t)i0 * nc, (size_t)nb * nc * sizeof(int64_t),
-                               cudaMemcpyHostToDevice, s));
+      M2M_CUDA(cudaMemcpyAsync(c->host_cond[k].p, h_cond + (size_t)i0 * nc, nb * nc * sizeof(int64_t),
+                               cudaMemcpyHostToDevice, cs));
     else
-      M2M_CUDA(cudaMemsetAsync(c->host_cond.p, 0, (size_t)nb * std::max(1, nc) * sizeof(int64_t), s));
+      M2M_CUDA(cudaMemsetAsync(c->host_cond[k].p, 0, nb * ncp * sizeof(int64_t), cs));
+    M2M_CUDA(cudaEventRecord(c->copy_ev[k], cs));
+    return 0;
+  };
+  M2M_TRY(upload(0));
+  for (int64_t chunk = 0; chunk < n_chunks; ++chunk) {
+    const int k = (int)(chunk & 1);
+    const int64_t i0 = chunk * device_batch;
+    const int nb = (int)std::min<int64_t>(device_batch, n_seg - i0);
+    M2M_CUDA(cudaStreamWaitEvent(s, c->copy_ev[k], 0));
+    // batch i-1 (which read the other staging buffer) finished inside the previous generate call (it synchronises)
+    if (chunk + 1 < n_chunks) M2M_TRY(upload(chunk + 1));
     int len = 0;
+    timing_begin(c);
     int rc = c->cfg.precision == M2M_BF16
-                 ? generate_impl<bf16>(c, c->host_wave.as<float>(), c->host_cond.as<int64_t>(), nb, S, max_length,
+                 ? generate_impl<bf16>(c, c->host_wave[k].as<float>(), c->host_cond[k].as<int64_t>(), nb, S, max_length,
                                        c->host_tokens.as<int64_t>(), &len, s)
-                 : generate_impl<float>(c, c->host_wave.as<float>(), c->host_cond.as<int64_t>(), nb, S, max_length,
+                 : generate_impl<float>(c, c->host_wave[k].as<float>(), c->host_cond[k].as<int64_t>(), nb, S, max_length,
                                         c->host_tokens.as<int64_t>(), &len, s);
     if (rc) return rc;
-    M2M_CUDA(cudaMemcpyAsync(h_tokens + (size_t)i0 * max_length, c->host_tokens.p,
-                             (size_t)nb * max_length * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    // token ids fit 16 bits (vocab 400): narrow on the device, read back a quarter of the int64 bytes, widen on the host
+    const size_t n_tok = (size_t)nb * max_length;
+    narrow_tokens_kernel<<<(unsigned)std::min<size_t>((n_tok + 255) / 256, 148 * 16), 256, 0, s>>>(
+        c->host_tokens.as<int64_t>(), c->host_tok16.as<int16_t>(), n_tok);
+    LAUNCH_CHECK(c);
+    M2M_CUDA(cudaMemcpyAsync(c->pinned_tok, c->host_tok16.p, n_tok * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
     M2M_CUDA(cudaStreamSynchronize(s));
+    int64_t* dst = h_tokens + (size_t)i0 * max_length;
+    for (size_t i = 0; i < n_tok; ++i) dst[i] = c->pinned_tok[i];
   }
   if (h_lens)
     for (int64_t i = 0; i < n_seg; ++i) {

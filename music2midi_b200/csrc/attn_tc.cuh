@@ -428,12 +428,8 @@ inline cudaError_t launch_seq_attn(const bf16* Q, int ldq, int B, int Lq, int H,
       !make_map_box64(&tv, V, kv_rows, (uint64_t)ld_kv, (uint64_t)ld_kv))
     return cudaErrorInvalidValue;
   const int smem = 1024 + 16384 + 3 * 16384 + 32768;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(seq_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  cudaError_t ae = ensure_smem_attr(reinterpret_cast<const void*>(seq_attn_tc_kernel), smem);
+  if (ae != cudaSuccess) return ae;
   dim3 grid((Lq + 127) / 128, H, B);
   seq_attn_tc_kernel<<<grid, 192, smem, stream>>>(tq, tk, tv, Lq, Lk, k_col0, v_col0, head_cols, rows_per_b, rows_per_h, O,
                                                   ldo, bias, bias_ld, bias_zero, causal ? 1 : 0);
@@ -461,12 +457,8 @@ inline cudaError_t launch_enc_attn(const bf16* qkv, int ld, int B, int L, int H,
   const uint32_t tmem_cols = (64 + NK) <= 256 ? 256u : 512u;
   const int region_a = nkb * 16384 > 16384 + nkb * 8192 ? nkb * 16384 : 16384 + nkb * 8192;
   const int smem = 1024 + region_a + nkb * 8192;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    smem_set = smem;
-  }
+  cudaError_t ae = ensure_smem_attr(reinterpret_cast<const void*>(enc_attn_tc_kernel), smem);
+  if (ae != cudaSuccess) return ae;
   dim3 grid((L + 127) / 128, H, B);
   enc_attn_tc_kernel<<<grid, 192, smem, stream>>>(tm, L, H * 64, O, ldo, bias, bias_ld, bias_zero, nkb, NK, tmem_cols);
   return cudaGetLastError();

@@ -202,38 +202,11 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, 
       : "memory");
 }
 
-// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
-// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor is still
-// running; it must call pdl_wait() before touching anything the predecessor wrote (and before writing anything the
-// predecessor may still read).  pdl_trigger() lets the *next* kernel start its own prologue.  Both are no-ops for
-// ordinary launches.  Used inside the decode-step graph to hide launch latency and kernel prologues.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 // gelu_new (tanh approximation), transformers NewGELUActivation
 __device__ __forceinline__ float gelu_new(float x) {
   const float k = 0.7978845608028654f;  // sqrt(2/pi)
   return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * (x * x * x))));
 }
 
-
-// host: launch with or without the PDL attribute (only for kernels that call pdl_wait())
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
-                            Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  if (pdl) {
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-  }
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
 
 }  // namespace m2m

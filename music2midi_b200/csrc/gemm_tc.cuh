@@ -16,6 +16,10 @@
 
 #include <cuda.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace m2m {
@@ -80,16 +84,11 @@ struct SmemLayout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */;
 };
 
-// RMS = true fuses T5's RMSNorm into the GEMM: A is the bf16 copy of the *un-normalised* residual stream (K must be
-// the whole row, K == d_model), the norm weight is folded into W on the host, and the epilogue warps - idle during
-// the main loop - read each A tile from shared memory as it lands, accumulate sum(x^2) of their row and finally scale
-// the accumulator row by rsqrt(mean(x^2) + eps):  C[m,:] = rstd[m] * sum_k x[m,k] (W[n,k] w_ln[k]).
-template <int BN, int STAGES, int NSPLIT, bool RMS, typename Epi>
+template <int BN, int STAGES, int NSPLIT, typename Epi>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
-                                                      int a_split_rows, int w_split_rows, float rms_eps, Epi epi,
+                                                      int a_split_rows, int w_split_rows, Epi epi,
                                                       const DecState* __restrict__ st) {
-  static_assert(!RMS || NSPLIT == 1, "fused RMSNorm needs plain bf16 operands");
   using L = SmemLayout<BN, STAGES, NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -105,7 +104,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], RMS ? 5 : 1);  // MMA commit (+ one arrival per epilogue warp that read the A tile)
+      mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
     mbar_fence_init();
@@ -124,10 +123,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
   }
-  // Everything above (barrier init, TMEM allocation, descriptor prefetch) touches no global data and may overlap the
-  // tail of the previous kernel under programmatic dependent launch; everything below depends on it.
-  pdl_wait();
-  pdl_trigger();
   const bool active = !(st != nullptr && st->done);  // finished decode: skip the work, still release TMEM
 
   if (!active) {
@@ -182,30 +177,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     // (32 columns); the 32x32 block is transposed through shared memory (the operand ring is idle by now) so
     // that 8 adjacent lanes cover 32 consecutive columns of one row: epilogue loads/stores are full sectors.
     const int q = warp & 3;
-    float rstd = 1.f;
-    if constexpr (RMS) {
-      // sum of squares of row (q*32 + lane) over all K, read from the A tiles in the operand ring.  A row is 128 B
-      // (8 swizzled 16-byte chunks); the order of the chunks is irrelevant for a sum, so no un-swizzling.
-      float ss = 0.f;
-      const int r = q * 32 + lane;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-        const uint8_t* arow = smem + s * L::STAGE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          float x8[8];
-          Vec16<bf16>::load_shared(reinterpret_cast<const bf16*>(arow + ch * 16), x8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) ss = fmaf(x8[e], x8[e], ss);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-      }
-      rstd = rsqrtf(ss / (float)K + rms_eps);
-      // the transposition tiles below alias operand-ring stage 0: every epilogue warp must be done reading A
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float(*tile)[36] = reinterpret_cast<float(*)[36]>(smem + q * (32 * 36 * 4));
@@ -215,10 +186,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       if (n0 + c0 >= N) break;  // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if constexpr (RMS) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * rstd);
-      }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<uint4*>(&tile[lane][4 * j]) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -279,52 +246,48 @@ inline bool supported(int M, int N, int K, int lda) {
   return M >= 1 && K % BK == 0 && N % 4 == 0 && lda % 8 == 0;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember what was set per (function, device), so a
+// second context on another GPU of the same process gets its own opt-in.
+inline cudaError_t ensure_smem_attr(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  int& cur = done[std::make_pair(func, dev)];
+  if (bytes > cur) {
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    cur = bytes;
+  }
+  return cudaSuccess;
+}
+
 // NSPLIT = 3: A is [3 * a_split_rows, K] and W is [3 * w_split_rows, K] (terms stacked along rows).
-template <int BN, int STAGES, typename Epi, int NSPLIT = 1, bool RMS = false>
+template <int BN, int STAGES, typename Epi, int NSPLIT = 1>
 inline cudaError_t launch_cfg(const bf16* A, int lda, const bf16* W, int M, int N, int K, Epi epi, const DecState* st,
-                              cudaStream_t stream, int a_split_rows = 0, int w_split_rows = 0, float rms_eps = 0.f,
-                              bool pdl = false) {
+                              cudaStream_t stream, int a_split_rows = 0, int w_split_rows = 0) {
   CUtensorMap ta, tw;
   const uint64_t a_rows = NSPLIT == 1 ? (uint64_t)M : (uint64_t)NSPLIT * a_split_rows;
   const uint64_t w_rows = NSPLIT == 1 ? (uint64_t)N : (uint64_t)NSPLIT * w_split_rows;
   if (!make_map(&ta, A, a_rows, (uint64_t)K, (uint64_t)lda, BM) || !make_map(&tw, W, w_rows, (uint64_t)K, (uint64_t)K, BN))
     return cudaErrorInvalidValue;
-  auto kern = gemm_tc_kernel<BN, STAGES, NSPLIT, RMS, Epi>;
+  auto kern = gemm_tc_kernel<BN, STAGES, NSPLIT, Epi>;
   constexpr int smem = SmemLayout<BN, STAGES, NSPLIT>::TOTAL;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(kern), smem);
+  if (e != cudaSuccess) return e;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  return launch_k(kern, grid, dim3(192), (size_t)smem, stream, pdl, ta, tw, M, N, K, a_split_rows, w_split_rows, rms_eps,
-                  epi, st);
+  kern<<<grid, 192, smem, stream>>>(ta, tw, M, N, K, a_split_rows, w_split_rows, epi, st);
+  return cudaGetLastError();
 }
 
-// lean = smaller operand rings (65 / 73 KB of shared memory) so that a GEMM CTA fits on an SM next to the
-// persistent decode-attention blocks of the other micro-batch.
 template <typename Epi>
 inline cudaError_t launch(const bf16* A, int lda, const bf16* W, int M, int N, int K, Epi epi, const DecState* st,
-                          cudaStream_t stream, int num_sms, bool lean = false, bool pdl = false) {
+                          cudaStream_t stream, int num_sms) {
   long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
-  if (tiles128 >= num_sms)
-    return lean ? launch_cfg<128, 2, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl)
-                : launch_cfg<128, 3, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl);
-  return lean ? launch_cfg<64, 3, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl)
-              : launch_cfg<64, 4, Epi>(A, lda, W, M, N, K, epi, st, stream, 0, 0, 0.f, pdl);
-}
-
-// fused RMSNorm + GEMM (K == d_model): A = bf16 residual stream, W = weights with the norm weight folded in
-template <typename Epi>
-inline cudaError_t launch_rms(const bf16* A, int lda, const bf16* W, int M, int N, int K, float eps, Epi epi,
-                              const DecState* st, cudaStream_t stream, int num_sms, bool lean = false) {
-  long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
-  if (tiles128 >= num_sms)
-    return lean ? launch_cfg<128, 2, Epi, 1, true>(A, lda, W, M, N, K, epi, st, stream, 0, 0, eps)
-                : launch_cfg<128, 3, Epi, 1, true>(A, lda, W, M, N, K, epi, st, stream, 0, 0, eps);
-  return lean ? launch_cfg<64, 3, Epi, 1, true>(A, lda, W, M, N, K, epi, st, stream, 0, 0, eps)
-              : launch_cfg<64, 4, Epi, 1, true>(A, lda, W, M, N, K, epi, st, stream, 0, 0, eps);
+  if (tiles128 >= num_sms) return launch_cfg<128, 3, Epi>(A, lda, W, M, N, K, epi, st, stream);
+  return launch_cfg<64, 4, Epi>(A, lda, W, M, N, K, epi, st, stream);
 }
 
 }  // namespace tc

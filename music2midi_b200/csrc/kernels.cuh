@@ -15,8 +15,6 @@ template <typename TO>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       TO* __restrict__ y, int rows, int D, float eps,
                                                       const DecState* __restrict__ st) {
-  pdl_wait();
-  pdl_trigger();
   if (st != nullptr && st->done) return;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -208,8 +206,6 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
                                                           T* __restrict__ out, int H,
                                                           const DecState* __restrict__ st,
                                                           const uint8_t* __restrict__ finished) {
-  pdl_wait();  // everything below depends on the previous kernels of the step (q, the appended K/V row, DecState)
-  pdl_trigger();
   if (st->done) return;
   const int h = blockIdx.x, b = blockIdx.y;
   if (finished != nullptr && finished[b]) return;
@@ -378,203 +374,6 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
   }
 }
 
-// Persistent variant of decode_attn_kernel for micro-batched decoding: a fixed grid (a few blocks per SM)
-// walks over the (row, head) items with a static stride, so the kernel never has pending blocks and leaves
-// shared memory / warp slots on every SM for the latency-bound GEMM chain of the *other* micro-batch, which runs
-// concurrently on its own stream.  The chunk stream is flattened across items: thread 0 keeps STAGES-1 bulk
-// copies in flight across item boundaries, so there is no pipeline bubble between items.
-template <typename T, bool SELF, bool FAST_EXP, int STAGES>
-__global__ void __launch_bounds__(128) decode_attn_persist_kernel(const T* __restrict__ q, const T* __restrict__ Kc,
-                                                                  const T* __restrict__ Vc, size_t row_stride,
-                                                                  size_t head_stride, int nkeys_fixed,
-                                                                  const float* __restrict__ bias, int bias_ld,
-                                                                  T* __restrict__ out, int H, int nb,
-                                                                  const DecState* __restrict__ st,
-                                                                  const uint8_t* __restrict__ finished) {
-  if (st->done) return;
-  constexpr int CHUNK_BYTES = 4096;
-  constexpr int CH = CHUNK_BYTES / (64 * (int)sizeof(T));
-  constexpr int VEC = Vec16<T>::N;
-  constexpr int LPK = 64 / VEC;
-  constexpr int KPI = 32 / LPK;
-  constexpr int SLICE = CH / 4;
-  constexpr int ITERS = SLICE / KPI;
-  __shared__ __align__(128) uint8_t ring[STAGES][2][CHUNK_BYTES];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ float part_acc[2][4][64];
-  __shared__ float part_m[2][4], part_l[2][4];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane / LPK, c = lane % LPK;
-  const int inner = H * 64;
-  const int t = st->t;
-  const int nkeys = SELF ? t + 1 : nkeys_fixed;
-  const int nchunks = (nkeys + CH - 1) / CH;
-  const int items = nb * H, G = gridDim.x;
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 4);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  auto next_valid = [&](int it) {
-    if (finished != nullptr)
-      while (it < items && finished[it / H]) it += G;
-    return it;
-  };
-
-  // producer cursor (thread 0 only)
-  int p_item = next_valid(blockIdx.x), p_chunk = 0;
-  uint32_t issued = 0, consumed = 0;
-  auto top_up = [&]() {  // keep STAGES-1 chunk copies in flight
-    while (p_item < items && issued < consumed + (STAGES - 1)) {
-      const int s = issued % STAGES;
-      const uint32_t u = issued / STAGES;
-      if (u > 0) mbar_wait(&empty_bar[s], (u - 1) & 1);
-      const int b = p_item / H, h = p_item - b * H;
-      const uint8_t* kg = reinterpret_cast<const uint8_t*>(Kc + (size_t)b * row_stride + (size_t)h * head_stride);
-      const uint8_t* vg = reinterpret_cast<const uint8_t*>(Vc + (size_t)b * row_stride + (size_t)h * head_stride);
-      const int nk = min(CH, nkeys - p_chunk * CH);
-      const uint32_t bytes = (uint32_t)nk * 64u * (uint32_t)sizeof(T);
-      mbar_expect_tx(&full_bar[s], 2 * bytes);
-      bulk_g2s(ring[s][0], kg + (size_t)p_chunk * CHUNK_BYTES, bytes, &full_bar[s]);
-      bulk_g2s(ring[s][1], vg + (size_t)p_chunk * CHUNK_BYTES, bytes, &full_bar[s]);
-      ++issued;
-      if (++p_chunk == nchunks) {
-        p_chunk = 0;
-        p_item = next_valid(p_item + G);
-      }
-    }
-  };
-  if (tid == 0) top_up();
-
-  int par = 0;
-  for (int item = next_valid(blockIdx.x); item < items; item = next_valid(item + G), par ^= 1) {
-    const int b = item / H, h = item - b * H;
-    float qv[VEC];
-    Vec16<T>::load(q + (size_t)b * inner + h * 64 + c * VEC, qv);
-    const float* bh = SELF ? bias + (size_t)h * bias_ld : nullptr;
-    float m = -INFINITY, l = 0.f, acc[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
-
-    for (int i = 0; i < nchunks; ++i) {
-      if (tid == 0) top_up();
-      const int s = consumed % STAGES;
-      mbar_wait(&full_bar[s], (consumed / STAGES) & 1);
-      const T* ks = reinterpret_cast<const T*>(ring[s][0]);
-      const T* vs = reinterpret_cast<const T*>(ring[s][1]);
-      float kv[ITERS][VEC], vv[ITERS][VEC];
-      const int nvalid = min(CH, nkeys - i * CH);
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int kl = min(warp * SLICE + it * KPI + g, nvalid - 1);
-        Vec16<T>::load_shared(ks + kl * 64 + c * VEC, kv[it]);
-        Vec16<T>::load_shared(vs + kl * 64 + c * VEC, vv[it]);
-      }
-      if constexpr (FAST_EXP) {  // same update as decode_attn_kernel (bit-identical results)
-        float sc[ITERS];
-        float mc = -INFINITY;
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-          const int j = i * CH + warp * SLICE + it * KPI + g;
-          float d = 0.f;
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) d = fmaf(qv[e], kv[it][e], d);
-#pragma unroll
-          for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-          if (SELF && j < nkeys) d += __ldg(bh + (t - j));
-          sc[it] = (j < nkeys) ? d : -INFINITY;
-          mc = fmaxf(mc, sc[it]);
-        }
-        if (mc > -INFINITY) {
-          const float mn = fmaxf(m, mc);
-          const float r = __expf(m - mn);
-          l *= r;
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) acc[e] *= r;
-#pragma unroll
-          for (int it = 0; it < ITERS; ++it) {
-            const float pw = __expf(sc[it] - mn);
-            l += pw;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] = fmaf(pw, vv[it][e], acc[e]);
-          }
-          m = mn;
-        }
-      } else {
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-          const int j = i * CH + warp * SLICE + it * KPI + g;
-          float sc = 0.f;
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) sc = fmaf(qv[e], kv[it][e], sc);
-#pragma unroll
-          for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-          if (j < nkeys) {
-            if (SELF) sc += __ldg(bh + (t - j));
-            const float mn = fmaxf(m, sc);
-            const float r = expf(m - mn);
-            const float pw = expf(sc - mn);
-            l = l * r + pw;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] = acc[e] * r + pw * vv[it][e];
-            m = mn;
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-      ++consumed;
-    }
-#pragma unroll
-    for (int o = LPK; o < 32; o <<= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-      const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
-      const float mn = fmaxf(m, m2);
-      const float s1 = (m == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m - mn) : expf(m - mn));
-      const float s2 = (m2 == -INFINITY) ? 0.f : (FAST_EXP ? __expf(m2 - mn) : expf(m2 - mn));
-      l = l * s1 + l2 * s2;
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], o);
-        acc[e] = acc[e] * s1 + a2 * s2;
-      }
-      m = mn;
-    }
-    if (g == 0) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) part_acc[par][warp][c * VEC + e] = acc[e];
-      if (c == 0) {
-        part_m[par][warp] = m;
-        part_l[par][warp] = l;
-      }
-    }
-    __syncthreads();  // partials of this item visible; buffers of parity `par` are reused two items later
-    if (warp == 0) {
-      const float mm = fmaxf(fmaxf(part_m[par][0], part_m[par][1]), fmaxf(part_m[par][2], part_m[par][3]));
-      float ll = 0.f, o0 = 0.f, o1 = 0.f;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const float pm = part_m[par][w];
-        const float sw = (pm == -INFINITY) ? 0.f : (FAST_EXP ? __expf(pm - mm) : expf(pm - mm));
-        ll += part_l[par][w] * sw;
-        o0 += part_acc[par][w][2 * lane] * sw;
-        o1 += part_acc[par][w][2 * lane + 1] * sw;
-      }
-      const float inv = 1.f / ll;
-      T* op = out + (size_t)b * inner + h * 64 + 2 * lane;
-      op[0] = from_f<T>(o0 * inv);
-      op[1] = from_f<T>(o1 * inv);
-    }
-  }
-}
-
 // torch.argmax order: NaN beats everything, then larger value, then lower index.
 __device__ __forceinline__ bool argmax_better(float v, int i, float best, int bi) {
   if (i == 0x7fffffff) return false;
@@ -583,6 +382,34 @@ __device__ __forceinline__ bool argmax_better(float v, int i, float best, int bi
   if (vn != bn) return vn;
   if (vn) return i < bi;
   return v > best || (v == best && i < bi);
+}
+
+// One embedding row -> fp32 residual stream (+ for the decode GEMM chain: its bf16 copy and the row's sum of squares
+// in ss[0], zeros in ss[1..ss_ld), the layout the chain's residual epilogues leave behind).  Whole block.
+__device__ __forceinline__ void embed_row(const float* __restrict__ src, float* __restrict__ x, bf16* __restrict__ xb,
+                                          float* __restrict__ ss, int ss_ld, int D) {
+  float part = 0.f;
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<float4*>(x)[i] = v;
+    if (xb != nullptr) {
+      const float o[4] = {v.x, v.y, v.z, v.w};
+      store4(xb + 4 * i, o);
+    }
+    part += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (ss != nullptr) {  // fixed-order block reduction (deterministic)
+    __shared__ float red[32];
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+      ss[0] = tot;
+      for (int i = 1; i < ss_ld; ++i) ss[i] = 0.f;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ greedy selection (a9)
@@ -594,9 +421,8 @@ __global__ void __launch_bounds__(128) select_token_kernel(const float* __restri
                                                            uint8_t* __restrict__ finished,
                                                            const float* __restrict__ table, float* __restrict__ x, int D,
                                                            float* __restrict__ logits_out, DecState* __restrict__ st,
-                                                           int pad_id, int eos_id, bf16* __restrict__ xb) {
-  pdl_wait();
-  pdl_trigger();
+                                                           int pad_id, int eos_id, bf16* __restrict__ xb,
+                                                           float* __restrict__ ss, int ss_ld) {
   if (st->done) return;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int t = st->t;
@@ -632,22 +458,12 @@ __global__ void __launch_bounds__(128) select_token_kernel(const float* __restri
     s_next = next < 0 ? 0 : (next >= V ? V - 1 : next);
   }
   __syncthreads();
-  const float4* src = reinterpret_cast<const float4*>(table + (size_t)s_next * D);
-  float4* dst = reinterpret_cast<float4*>(x + (size_t)b * D);
-  for (int i = tid; i < D / 4; i += 128) {
-    const float4 v = src[i];
-    dst[i] = v;
-    if (xb != nullptr) {  // bf16 copy of the residual stream for the fused RMSNorm-GEMMs
-      const float o[4] = {v.x, v.y, v.z, v.w};
-      store4(xb + (size_t)b * D + 4 * i, o);
-    }
-  }
+  embed_row(table + (size_t)s_next * D, x + (size_t)b * D, xb ? xb + (size_t)b * D : nullptr,
+            ss ? ss + (size_t)b * ss_ld : nullptr, ss_ld, D);
 }
 
 // advances the step counter; detects "all rows finished" / length cap.  <<<1,1>>>
 __global__ void step_advance_kernel(DecState* st, int greedy_stop) {
-  pdl_wait();
-  pdl_trigger();
   if (st->done) return;
   int t = st->t + 1;  // tokens generated so far = t (excluding BOS) -> sequence length t + 1
   st->t = t;
@@ -743,6 +559,12 @@ __global__ void __launch_bounds__(512) mel_band_log_kernel(const float* __restri
       out[m * n_mels + j] = logf(fmaxf(acc, 1e-6f));
     }
   }
+}
+
+// int64 token ids -> int16 (vocabulary 400): the host read-back moves a quarter of the bytes
+__global__ void narrow_tokens_kernel(const int64_t* __restrict__ in, int16_t* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (int16_t)in[i];
 }
 
 // fp32 -> T copy (n4 = number of 4-element groups)

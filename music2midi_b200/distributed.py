@@ -29,27 +29,44 @@ def shard_clips(n_clips: int, segments_per_clip: int, rank: int, world: int) -> 
     return lo * segments_per_clip, hi * segments_per_clip
 
 
-def gather_tokens(local_tokens: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
-    """All-gather of per-rank token blocks [n_local, L] (any integer dtype) into [n_total, L] int64 in
-    global segment order.  Blocks may differ in size by one clip: ranks pad to the largest block."""
+def gather_tokens(local_tokens: torch.Tensor, n_total: int, group=None, counts: Optional[List[int]] = None,
+                  out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """All-gather of per-rank token blocks [n_local, L] (any integer dtype) into [n_total, L] in global segment
+    order.  ONE collective when `counts` (rows held by every rank) is known or every rank holds n_total / world
+    rows; otherwise a second, tiny one exchanges the counts first.  Token ids travel as int16 (vocabulary 400) and
+    are only widened if `out_dtype` asks for it."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return local_tokens.to(torch.int64)
+        return local_tokens.to(out_dtype)
     world = dist.get_world_size(group)
     L = local_tokens.shape[1]
-    n_local = torch.tensor([local_tokens.shape[0]], dtype=torch.int64, device=local_tokens.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
+    if counts is None and n_total == world * local_tokens.shape[0]:
+        # contiguous block sharding differs by at most one clip between ranks: if this rank holds exactly
+        # n_total / world rows, every rank does
+        counts = [local_tokens.shape[0]] * world
+    if counts is None:
+        n_local = torch.tensor([local_tokens.shape[0]], dtype=torch.int64, device=local_tokens.device)
+        got = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(got, n_local, group=group)
+        counts = [int(c) for c in got]
     counts = [int(c) for c in counts]
-    if sum(counts) != n_total:
+    if len(counts) != world or sum(counts) != n_total:
         raise RuntimeError(f"token gather: ranks hold {sum(counts)} rows, expected {n_total}")
+    if counts[dist.get_rank(group)] != local_tokens.shape[0]:
+        raise RuntimeError("token gather: counts do not match this rank's block")
     width = max(counts)
-    send = torch.zeros(width, L, dtype=torch.int16, device=local_tokens.device)
-    send[: local_tokens.shape[0]] = local_tokens.to(torch.int16)
+    if local_tokens.dtype == torch.int16 and local_tokens.shape[0] == width and local_tokens.is_contiguous():
+        send = local_tokens
+    else:
+        send = torch.zeros(width, L, dtype=torch.int16, device=local_tokens.device)
+        send[: local_tokens.shape[0]] = local_tokens.to(torch.int16)
     recv = torch.empty(world * width, L, dtype=torch.int16, device=local_tokens.device)
     # transported as raw bytes: gloo (CPU tests) has no int16 collectives, NCCL does not care
     dist.all_gather_into_tensor(recv.view(torch.uint8), send.view(torch.uint8), group=group)
-    parts = [recv[r * width: r * width + counts[r]] for r in range(world)]
-    return torch.cat(parts, dim=0).to(torch.int64)
+    if all(c == width for c in counts):
+        out = recv
+    else:
+        out = torch.cat([recv[r * width: r * width + counts[r]] for r in range(world)], dim=0)
+    return out if out_dtype == torch.int16 else out.to(out_dtype)
 
 
 def transcribe_sharded(generate_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], segments: torch.Tensor,

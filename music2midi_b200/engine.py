@@ -212,12 +212,14 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ introspection
-    def set_flags(self, graph: bool = True, time_attention: bool = False, skip_finished: bool = True,
+    def set_flags(self, graph: bool = True, time_classes: bool = False, skip_finished: bool = True,
                   no_tensor_cores: bool = False, mel: str = "auto", no_tc_attention: bool = False,
-                  microbatches: int = 0, fused_rmsnorm: bool = False, pdl: bool = False):
-        """mel: "auto" (tcgen05 DFT in bf16 contexts, fp32 CUDA-core DFT in fp32 contexts), "simt" or "tc"."""
-        f = (1 if graph else 0) | (2 if time_attention else 0) | (4 if skip_finished else 0) | (8 if no_tensor_cores else 0)
-        f |= {"auto": 0, "simt": 16, "tc": 32}[mel] | (64 if no_tc_attention else 0) | ((microbatches & 0xF) << 8) | (128 if fused_rmsnorm else 0) | (4096 if pdl else 0)
+                  no_chain: bool = False):
+        """mel: "auto" (tcgen05 DFT in bf16 contexts, fp32 CUDA-core DFT in fp32 contexts), "simt" or "tc".
+        time_classes: instrumented pass (CUDA events around every launch group, summed per kernel class).
+        no_chain: bf16 contexts run the decode step as separate RMSNorm / GEMM launches (A/B testing)."""
+        f = (1 if graph else 0) | (2 if time_classes else 0) | (4 if skip_finished else 0) | (8 if no_tensor_cores else 0)
+        f |= {"auto": 0, "simt": 16, "tc": 32}[mel] | (64 if no_tc_attention else 0) | (128 if no_chain else 0)
         check(self.lib.m2m_set_flags(self._ctx, f))
 
     def stats(self, reset: bool = False) -> Dict[str, float]:
@@ -225,7 +227,10 @@ class Engine:
         check(self.lib.m2m_stats_get(self._ctx, C.byref(s)))
         if reset:
             check(self.lib.m2m_stats_reset(self._ctx))
-        return {k: getattr(s, k) for k, _ in s._fields_}
+        out = {k: getattr(s, k) for k, _ in s._fields_ if not k.startswith("class_")}
+        out["class_ms"] = {n: s.class_ms[i] for i, n in enumerate(_lib.KERNEL_CLASSES)}
+        out["class_launches"] = {n: int(s.class_launches[i]) for i, n in enumerate(_lib.KERNEL_CLASSES)}
+        return out
 
 
 __all__ = ["Engine", "M2MError", "relative_position_bucket"]

@@ -9,7 +9,10 @@ Tolerances (stated once, used below):
                   any fp32 implementation; the per-case reference-vs-fp64 deviation is in mel.npz.
   ENC_TOL         max|d| / max|ref| <= 2e-4 for the fp32 encoder output
   LOGIT_TOL_FP32  max|d| <= 2e-3 absolute on logits (scale ~ +-8) in fp32 mode
-  LOGIT_TOL_BF16  max|d| <= 0.25 absolute and mean|d| <= 0.04 in bf16 mode (bf16 operands, fp32 accumulate)
+  LOGIT_TOL_BF16  max|d| <= 0.1 absolute and mean|d| <= 0.02 in bf16 mode (bf16 operands, fp32 accumulate; measured
+                  0.046 / 0.008 in round 1), and the argmax of the logits agrees with the reference's at >= 98 % of
+                  the golden (row, step) pairs; bf16 greedy tokens may leave the reference only where the reference's
+                  own top-2 logit gap is below 2 x LOGIT_TOL_BF16 (a near-tie at bf16 resolution)
   tokens          bit-exact in fp32 mode on rows whose golden top-2 logit gap is >= 2e-3 along the whole
                   path; on the remaining rows the first divergence must sit at a golden gap < 1e-3.
 """
@@ -27,8 +30,9 @@ MEL_TOL_NOISE = 1e-4
 MEL_TOL_TONES = 1e-3
 ENC_TOL = 2e-4
 LOGIT_TOL_FP32 = 2e-3
-LOGIT_TOL_BF16_MAX = 0.25
-LOGIT_TOL_BF16_MEAN = 0.04
+LOGIT_TOL_BF16_MAX = 0.1
+LOGIT_TOL_BF16_MEAN = 0.02
+ARGMAX_AGREEMENT_BF16 = 0.98
 STRICT_GAP = 2e-3
 TIE_GAP = 1e-3
 
@@ -193,6 +197,28 @@ def test_decode_logits_bf16(engine_bf16, cpu_embeds, report):
     agree = float((logits[:, steps].argmax(-1) == torch.from_numpy(g["logits"]).argmax(-1)).float().mean())
     report(test="decode_logits_bf16", max_abs=float(d.max()), mean_abs=float(d.mean()), argmax_agreement=agree)
     assert float(d.max()) <= LOGIT_TOL_BF16_MAX and float(d.mean()) <= LOGIT_TOL_BF16_MEAN
+    assert agree >= ARGMAX_AGREEMENT_BF16
+
+
+def test_decode_logits_bf16_chain_vs_separate_launches(engine_bf16, cpu_embeds, report):
+    """The cluster-phased GEMM chain (folded RMSNorm, chain_tc.cuh) against the same decode step run as separate
+    RMSNorm + GEMM launches: two bf16 evaluations of the same arithmetic, both inside the bf16 tolerance of the
+    reference and within bf16 rounding noise of each other."""
+    g = golden("generate.npz")
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))[:, :256]
+    steps = [s for s in g["logit_steps"].tolist() if s < 255]
+    ref = torch.from_numpy(g["logits"])[:, : len(steps)]
+    a = _forced_logits(engine_bf16, cpu_embeds, tokens)
+    engine_bf16.set_flags(no_chain=True)
+    b = _forced_logits(engine_bf16, cpu_embeds, tokens)
+    engine_bf16.set_flags()
+    d = (a - b).abs()
+    da, db = (a[:, steps] - ref).abs(), (b[:, steps] - ref).abs()
+    report(test="decode_logits_bf16_chain_vs_separate", max_abs=float(d.max()), mean_abs=float(d.mean()),
+           chain_vs_ref_max=float(da.max()), separate_vs_ref_max=float(db.max()),
+           chain_vs_ref_mean=float(da.mean()), separate_vs_ref_mean=float(db.mean()))
+    assert float(d.max()) <= LOGIT_TOL_BF16_MAX and float(d.mean()) <= LOGIT_TOL_BF16_MEAN
+    assert float(da.max()) <= LOGIT_TOL_BF16_MAX and float(db.max()) <= LOGIT_TOL_BF16_MAX
 
 
 # ------------------------------------------------------------------------------ decode: greedy tokens
@@ -306,7 +332,11 @@ def test_bf16_greedy_is_self_consistent(engine_bf16, cpu_embeds, report):
     out = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 1024).cpu()
     match = [int((out[r] != tokens[r]).nonzero()[0]) if not torch.equal(out[r], tokens[r]) else 1024
              for r in range(16)]
-    report(test="greedy_tokens_bf16", first_divergence=match)
+    gap = torch.from_numpy(g["gap"])
+    gaps = [None if m == 1024 else float(gap[r, m - 1]) for r, m in enumerate(match)]
+    report(test="greedy_tokens_bf16", first_divergence=match, golden_gap_at_divergence=gaps)
+    for r, (m, gp) in enumerate(zip(match, gaps)):  # bf16 may only leave the reference at a near-tie
+        assert gp is None or gp <= 2 * LOGIT_TOL_BF16_MAX, f"row {r} diverges at step {m} where the golden gap is {gp}"
     engine_bf16.set_flags(graph=False)
     out2 = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 1024).cpu()
     engine_bf16.set_flags(graph=True)
@@ -348,25 +378,6 @@ def test_transcribe_host_matches_device_api(engine_fp32):
     toks0, _ = engine_fp32.transcribe_host(wave.numpy(), None, 64, device_batch=8)
     dev0 = engine_fp32.generate(wave.to(DEV), torch.zeros_like(cond).to(DEV), 64).cpu().numpy()
     assert np.array_equal(toks0, dev0)
-
-
-# ------------------------------------------------------------------------------ micro-batched decode
-@pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_microbatched_persistent_decode_is_bit_identical(engine_bf16, engine_fp32, precision):
-    """>= 256 rows: the decode loop may run as independent micro-batches (persistent attention kernel, lean GEMM
-    rings, one CUDA graph and stream each).  Same arithmetic in the same order -> identical tokens."""
-    eng = engine_bf16 if precision == "bf16" else engine_fp32
-    wave = torch.cat([syn.audio_noise(150, 31), syn.audio_tones(150, 31)]).to(DEV)
-    cond = (torch.arange(600).reshape(300, 2) % 3).to(DEV)
-    eng.set_flags(microbatches=1)
-    a = eng.generate(wave, cond, 40)
-    outs = []
-    for n in (2, 3):
-        eng.set_flags(microbatches=n)
-        outs.append(eng.generate(wave, cond, 40))
-    eng.set_flags()
-    for o in outs:
-        assert torch.equal(a, o)
 
 
 # ------------------------------------------------------------------------------ full benchmark batch size
@@ -421,16 +432,42 @@ def test_generate_batch_sizes(engine_fp32, cpu_embeds, batch):
     assert torch.equal(out, tokens[idx, :20])
 
 
-def test_programmatic_dependent_launch_is_bit_identical(engine_bf16, cpu_embeds):
-    """PDL between the kernels of the decode step (graph and plain launches) must not change a single token."""
-    wave = torch.cat([syn.audio_noise(150, 33), syn.audio_tones(150, 33)]).to(DEV)
-    cond = (torch.arange(600).reshape(300, 2) % 3).to(DEV)
-    engine_bf16.set_flags()
-    ref_small = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 300)
-    ref_big = engine_bf16.generate(wave, cond, 64)
-    for graph in (True, False):
-        engine_bf16.set_flags(graph=graph, pdl=True)
-        a = engine_bf16.generate_from_embeds(cpu_embeds.to(DEV), 300)
-        b = engine_bf16.generate(wave, cond, 64)
-        engine_bf16.set_flags()
-        assert torch.equal(a, ref_small) and torch.equal(b, ref_big), f"graph={graph}"
+@pytest.mark.parametrize("batch", [1, 5, 127, 129, 300])
+def test_bf16_batch_sizes_are_batch_invariant(engine_bf16, batch):
+    """bf16 decode chain (one 6-CTA cluster per 128 rows, ragged last tile): a row's tokens are the same in every batch."""
+    wave, cond = candidate_inputs()
+    base = engine_bf16.generate(wave.to(DEV), cond.to(DEV), 40).cpu()
+    idx = torch.arange(batch) % 16
+    out = engine_bf16.generate(wave[idx].to(DEV), cond[idx].to(DEV), 40).cpu()
+    assert torch.equal(out, base[idx])
+
+
+# ------------------------------------------------------------------------------ benchmark shape: 2560 rows x 1024 tokens
+def test_benchmark_shape_fp32_matches_golden_tokens(engine_fp32, report):
+    """The BASELINE workload itself (2560 segments decoded to 1024 tokens in ONE device batch, 76 GB of fp32 KV
+    cache): the 16 golden inputs sit at fixed rows of the batch and must reproduce the reference's 1024 tokens."""
+    g = golden("generate.npz")
+    wave16, cond16 = candidate_inputs()
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    rows = torch.arange(16) * 160 + 7
+    wave = syn.audio_noise(2560, 4242)
+    cond = torch.zeros(2560, 2, dtype=torch.long)
+    wave[rows], cond[rows] = wave16, cond16
+    out = engine_fp32.generate(wave.to(DEV), cond.to(DEV), 1024)
+    assert out.shape == (2560, 1024)
+    _check_tokens(out[rows.to(DEV)].cpu(), tokens, torch.from_numpy(g["gap"]), report, "benchmark_shape_fp32_2560x1024")
+
+
+def test_benchmark_shape_bf16_is_batch_invariant(engine_bf16, report):
+    """bf16 at the benchmark shape (38 GB KV cache, size_t offsets): rows equal the same inputs decoded in a
+    16-row batch, over all 1024 tokens."""
+    wave16, cond16 = candidate_inputs()
+    small = engine_bf16.generate(wave16.to(DEV), cond16.to(DEV), 1024).cpu()
+    rows = torch.arange(16) * 160 + 7
+    wave = syn.audio_noise(2560, 4242)
+    cond = torch.zeros(2560, 2, dtype=torch.long)
+    wave[rows], cond[rows] = wave16, cond16
+    out = engine_bf16.generate(wave.to(DEV), cond.to(DEV), 1024)
+    big = out[rows.to(DEV)].cpu()
+    report(test="benchmark_shape_bf16_2560x1024", rows_equal=int((big == small).all(dim=1).sum()))
+    assert torch.equal(big, small)
