@@ -145,6 +145,13 @@ int m2m_transcribe_host(m2m_ctx* ctx, const float* h_wave, int64_t n_seg, int S,
 int m2m_tokens_to_notes(const int64_t* tokens, int64_t n_tokens, int64_t start_idx, int32_t pitch_offset,
                         int32_t time_offset, int32_t velocity, int64_t* out_rows4, int64_t cap, int64_t* n_notes);
 
+/* The same for a whole token matrix [n_rows, row_len] (row i starts at start_idx0 + i * steps_per_row: the
+ * "sequential" mode of MidiTokenizer.decode, music2midi/tokenizer.py:75-83; steps_per_row = 0 = "batched" mode).
+ * Note rows of all token rows are concatenated; row_note_end[i] (optional) = number of note rows after row i. */
+int m2m_tokens_to_notes_batch(const int64_t* tokens, int64_t n_rows, int64_t row_len, int64_t start_idx0,
+                              int64_t steps_per_row, int32_t pitch_offset, int32_t time_offset, int32_t velocity,
+                              int64_t* out_rows4, int64_t cap, int64_t* row_note_end, int64_t* n_notes);
+
 /* ------------------------------------------------------------------ introspection (bench / tests) */
 typedef struct m2m_stats {
   int64_t kernel_launches;   /* kernels launched (or replayed through graphs) since reset */
@@ -192,6 +199,11 @@ int m2m_set_flags(m2m_ctx* ctx, uint32_t flags);
  * Synchronises the stream, so a faulting kernel is reported by this call. */
 int m2m_debug_gemm_bf16(m2m_ctx* ctx, const void* d_A, const void* d_W, int M, int N, int K, float* d_C, int path,
                         void* stream);
+
+/* Profiling hook (tools/chain_trace.py): with M2M_CHAIN_TRACE=1 in the environment the decode GEMM-chain kernels of
+ * four launches per step (K0, KB[0], KA[0], KA[last]) leave clock64 stamps of their phase milestones per CTA; this
+ * copies them out as [4][*grid][*slots] (slot meanings: csrc/chain_tc.cuh). */
+int m2m_debug_chain_trace(m2m_ctx* ctx, long long* h_out, int64_t cap, int* grid, int* slots);
 
 #ifdef __cplusplus
 }

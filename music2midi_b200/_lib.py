@@ -67,9 +67,12 @@ SYMBOLS = {
     "m2m_transcribe_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "m2m_tokens_to_notes": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
                                       C.POINTER(C.c_int64)]),
+    "m2m_tokens_to_notes_batch": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                            _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     "m2m_stats_reset": (C.c_int, [_P]),
     "m2m_stats_get": (C.c_int, [_P, C.POINTER(Stats)]),
     "m2m_set_flags": (C.c_int, [_P, C.c_uint32]),
+    "m2m_debug_chain_trace": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "m2m_debug_gemm_bf16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
 }
 
@@ -99,9 +102,39 @@ def load() -> C.CDLL:
         return lib
 
 
+NOTES_LIB_PATH = os.path.join(HERE, "libm2m_notes.so")
+_notes_lib: Optional[C.CDLL] = None
+
+
+def load_notes() -> C.CDLL:
+    """The token -> notes state machine (csrc/notes.cpp).  It is part of libm2m_b200.so; where that library has not been
+    built (no nvcc: dataset tooling, CI) the same source compiled with g++ alone (libm2m_notes.so) is used, so the
+    tokenizer - integer CPU code in the reference too - does not depend on the CUDA toolchain."""
+    global _notes_lib
+    if _lib is not None:
+        return _lib
+    if os.path.exists(LIB_PATH):
+        return load()
+    with _lock:
+        if _notes_lib is None:
+            if not os.path.exists(NOTES_LIB_PATH):
+                from . import build as _build
+
+                _build.build_notes()
+            lib = C.CDLL(NOTES_LIB_PATH)
+            for name in ("m2m_tokens_to_notes", "m2m_tokens_to_notes_batch"):
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = SYMBOLS[name]
+            lib.m2m_notes_last_error.restype = C.c_char_p
+            lib.m2m_last_error = lib.m2m_notes_last_error
+            _notes_lib = lib
+        return _notes_lib
+
+
 def check(status: int) -> None:
     if status != 0:
-        raise M2MError(status, load().m2m_last_error().decode("utf-8", "replace"))
+        lib = _lib if _lib is not None else (_notes_lib if _notes_lib is not None else load())
+        raise M2MError(status, lib.m2m_last_error().decode("utf-8", "replace"))
 
 
 def default_config() -> Config:

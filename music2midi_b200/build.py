@@ -57,5 +57,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+NOTES_LIB = os.path.join(HERE, "libm2m_notes.so")
+
+
+def build_notes() -> str:
+    """Host-only build of the token -> notes state machine (g++, no CUDA): libm2m_notes.so."""
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if not cxx:
+        raise RuntimeError("g++ not found (needed to build libm2m_notes.so)")
+    cmd = [cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-DM2M_NOTES_STANDALONE", os.path.join(CSRC, "notes.cpp"), "-o", NOTES_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed on notes.cpp")
+    return NOTES_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

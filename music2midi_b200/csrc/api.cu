@@ -130,6 +130,8 @@ struct m2m_ctx {
   DevBuf mel_power, mel_a3, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
   DevBuf ckv, skv;  // cross / self KV caches, all layers
   DevBuf dec_xb, dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err, dec_ss;
+  DevBuf chain_trace;  // M2M_CHAIN_TRACE=1: clock64 stamps of four chain launches per step (K0, KB[0], KA[0], KA[last])
+  int chain_trace_grid = 0;
   DevBuf tf_x, tf_h, tf_qkv, tf_ao, tf_g, tf_q;  // teacher-forced decoder
   DevBuf host_wave[2], host_cond[2], host_tokens, host_tok16;  // m2m_transcribe_host device staging (double-buffered)
   int16_t* pinned_tok = nullptr;                 // pinned host landing buffer of the int16 token read-back
@@ -485,6 +487,7 @@ static int build_chain_plan(m2m_ctx* c, int B, int L, int max_length, float* log
     P.inv_d = 1.f / (float)D;
     P.ss = ss;
     P.st = st;
+    P.trace_phase = getenv("M2M_CHAIN_TRACE_PHASE") ? atoi(getenv("M2M_CHAIN_TRACE_PHASE")) : 2;
   };
   auto residual = [&](tc::ChainPhase* ph, const bf16* A, int K, const void* W) {
     bool ok = tc::chain_phase(ph, A, B, K, (const bf16*)W, D, 1, 64, D, tc::CH_RESIDUAL);
@@ -504,8 +507,19 @@ static int build_chain_plan(m2m_ctx* c, int B, int L, int max_length, float* log
     ph->inner = I;
     return ok;
   };
+  long long* trace = nullptr;
+  if (getenv("M2M_CHAIN_TRACE")) {
+    const int grid = tc::CHAIN_CS * ((B + tc::BM - 1) / tc::BM);
+    if (c->chain_trace.ensure((size_t)4 * grid * tc::CHAIN_TRACE_SLOTS * sizeof(long long), nullptr) == 0) {
+      cudaMemset(c->chain_trace.p, 0, (size_t)4 * grid * tc::CHAIN_TRACE_SLOTS * sizeof(long long));
+      trace = c->chain_trace.as<long long>();
+      c->chain_trace_grid = grid;
+    }
+  }
+  auto trace_slot = [&](int k) { return trace ? trace + (size_t)k * c->chain_trace_grid * tc::CHAIN_TRACE_SLOTS : nullptr; };
   bool ok = true;
   base(plan->k0, 1);
+  plan->k0.trace = trace_slot(0);
   ok = ok && qkv(&plan->k0.ph[0], 0);
   plan->kb.resize(g.n_layers);
   plan->ka.resize(g.n_layers);
@@ -517,10 +531,13 @@ static int build_chain_plan(m2m_ctx* c, int B, int L, int max_length, float* log
     ok = ok && tc::chain_phase(&kb.ph[1], xb, B, D, w.wcq_ln, 96 * tc::CHAIN_CS, 1, 96, I, tc::CH_STORE);
     kb.ph[1].out0 = q;
     kb.ph[1].ld = I;
+    if (l == 0) kb.trace = trace_slot(1);
     tc::ChainParams& ka = plan->ka[l];
     base(ka, 4);
+    if (l == 0) ka.trace = trace_slot(2);
+    if (l == g.n_layers - 1) ka.trace = trace_slot(3);
     ok = ok && residual(&ka.ph[0], ao, I, w.wco);
-    ok = ok && tc::chain_phase(&ka.ph[1], xb, B, D, w.wi_ln, 2 * F, 2, 192, 2 * F, tc::CH_GELU);
+    ok = ok && tc::chain_phase(&ka.ph[1], xb, B, D, w.wi_ln, 2 * F, 3, 128, 2 * F, tc::CH_GELU);
     ka.ph[1].out0 = gg;
     ka.ph[1].ld = F;
     ok = ok && residual(&ka.ph[2], gg, F, w.wffo);
@@ -629,7 +646,7 @@ static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const in
   }
   TimedScope ts(c, KC_DEC_SELECT, s, step);
   select_token_kernel<<<B, 128, 0, s>>>(logits, V, tokens, max_length, forced, fin, c->shared, x, D, logits_all, st,
-                                        g.pad_id, g.eos_id, xb, ss, ss ? tc::CHAIN_CS : 0);
+                                        g.pad_id, g.eos_id, xb, ss, ss ? tc::CHAIN_SS : 0);
   LAUNCH_CHECK(c);
   step_advance_kernel<<<1, 1, 0, s>>>(st, forced == nullptr ? 1 : 0);
   LAUNCH_CHECK(c);
@@ -680,7 +697,7 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   M2M_TRY(c->skv.ensure((size_t)g.n_layers * 2 * B * max_length * I * sizeof(T), &c->generation));
   M2M_TRY(c->dec_x.ensure((size_t)B * D * sizeof(float), &c->generation));
   M2M_TRY(c->dec_xb.ensure((size_t)B * D * sizeof(bf16), &c->generation));
-  M2M_TRY(c->dec_ss.ensure((size_t)B * tc::CHAIN_CS * sizeof(float), &c->generation));
+  M2M_TRY(c->dec_ss.ensure((size_t)B * tc::CHAIN_SS * sizeof(float), &c->generation));
   M2M_TRY(c->dec_h.ensure((size_t)B * D * sizeof(T), &c->generation));
   M2M_TRY(c->dec_q.ensure((size_t)B * I * sizeof(T), &c->generation));
   M2M_TRY(c->dec_ao.ensure((size_t)B * I * sizeof(T), &c->generation));
@@ -705,7 +722,7 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   decode_init_kernel<<<B, 128, 0, s>>>(tokens, max_length, c->dec_finished.as<uint8_t>(), c->dec_x.as<float>(), c->shared,
                                        D, B, g.bos_id, c->dec_state.as<DecState>(), max_length,
                                        chain_mode ? c->dec_xb.as<bf16>() : nullptr,
-                                       chain_mode ? c->dec_ss.as<float>() : nullptr, tc::CHAIN_CS);
+                                       chain_mode ? c->dec_ss.as<float>() : nullptr, tc::CHAIN_SS);
   LAUNCH_CHECK(c);
 
   if (use_graph && n_steps > 0) {
@@ -1074,7 +1091,7 @@ int m2m_ctx_destroy(m2m_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
                     &c->enc_out, &c->ckv, &c->skv, &c->dec_xb, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
-                    &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->dec_ss, &c->tf_x, &c->tf_h,
+                    &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->dec_ss, &c->chain_trace, &c->tf_x, &c->tf_h,
                     &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave[0], &c->host_wave[1], &c->host_cond[0],
                     &c->host_cond[1], &c->host_tokens, &c->host_tok16};
   for (DevBuf* b : bufs) b->release();
@@ -1537,6 +1554,19 @@ int m2m_debug_gemm_bf16(m2m_ctx* c, const void* d_A, const void* d_W, int M, int
     return M2M_ERR_CUDA;
   }
   M2M_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int m2m_debug_chain_trace(m2m_ctx* c, long long* h_out, int64_t cap, int* grid, int* slots) {
+  if (!c || !grid || !slots) { set_error("null argument"); return M2M_ERR_INVALID; }
+  M2M_TRY(ensure_device(c));
+  *grid = c->chain_trace_grid;
+  *slots = tc::CHAIN_TRACE_SLOTS;
+  const size_t n = (size_t)4 * c->chain_trace_grid * tc::CHAIN_TRACE_SLOTS;
+  if (n == 0 || !c->chain_trace.p) return 0;
+  M2M_REQUIRE(h_out && (size_t)cap >= n, "trace buffer too small: need %zu entries", n);
+  M2M_CUDA(cudaDeviceSynchronize());
+  M2M_CUDA(cudaMemcpy(h_out, c->chain_trace.p, n * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

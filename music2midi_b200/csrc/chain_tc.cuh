@@ -8,13 +8,18 @@
 // cluster-scope mbarrier handshake (remote mbarrier arrives, ~0.3 us) instead of a kernel boundary (launch + drain
 // + TMEM alloc + pipeline fill, 6-15 us each in round 1).  One launch runs up to four phases.
 //
-//   warp 0      : A producer  - TMA loads of the 128 x 64 activation tiles (6-deep ring); waits for the phase
-//                 handshake, because A of phase p is the output of phase p-1 of ALL six CTAs
-//   warp 1      : B producer  - TMA loads of the weight sub-tiles (5-deep ring of 24 KB slots); weights depend on
+//   warp 0      : A producer  - the six CTAs of a cluster consume the SAME 128 x 64 activation tiles, so every tile
+//                 is fetched from L2 once and MULTICAST into the six shared memories (cp.async.bulk.tensor
+//                 .multicast::cluster): the ring has six stages and CTA r owns stage r of everybody's ring - it issues
+//                 tiles r, r + 6, ... after all six MMA issuers released the stage (tcgen05.commit multicast onto its
+//                 a_empty barrier).  Waits for the phase handshake: A of phase p is the output of phase p-1 of ALL CTAs
+//   warp 1      : B producer  - TMA loads of the weight sub-tiles (5-deep ring of 16 KB slots); weights depend on
 //                 nothing, so this warp free-runs ahead across phase boundaries (prefetch under the handshake)
 //   warp 2      : MMA issuer  - one lane, tcgen05.mma cta_group::1 kind::f16, M = 128, N = sub-tile rows, fp32
 //                 accumulators in TMEM (<= 384 columns per phase)
-//   warps 3-6   : epilogue    - tcgen05.ld (thread = row), fused epilogue, global stores, phase handshake
+//   warps 3-10  : epilogue    - two warps per TMEM lane quarter, each half of the columns: tcgen05.ld (thread = row),
+//                 32 x 32 transposition through shared memory so that 8 adjacent lanes cover 32 consecutive columns
+//                 of one row (full-sector global accesses), fused epilogue, phase handshake
 //
 // RMSNorm is folded: the norm weight is multiplied into W on the host (W'[n,k] = W[n,k] ln[k]) and the A operand
 // is the bf16 copy of the UN-normalised residual stream; the residual epilogues leave one partial sum of squares
@@ -34,12 +39,18 @@ namespace tc {
 
 constexpr int CHAIN_CS = 6;
 constexpr int CHAIN_MAX_PHASES = 4;
-constexpr int CHAIN_A_STAGES = 6;
-constexpr int CHAIN_B_STAGES = 5;
+constexpr int CHAIN_A_STAGES = CHAIN_CS;  // stage r of every CTA's ring is filled by CTA r (multicast)
+constexpr int CHAIN_B_STAGES = 7;
+constexpr int CHAIN_EPI_WARPS = 8;   // two warps per TMEM lane quarter (each takes half of the phase's columns)
+constexpr int CHAIN_SS = 2 * CHAIN_CS;  // partial sums of squares per row: one per (column slice, epilogue half)
+constexpr int CHAIN_STAGE_BYTES = 32 * 36 * 4;  // per epilogue warp: 32 x 32 fp32 transposition tile, padded rows
 constexpr int CHAIN_A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int CHAIN_B_ROWS = 192;            // largest weight sub-tile
-constexpr int CHAIN_B_BYTES = CHAIN_B_ROWS * BK * 2;  // 24 KB
-constexpr int CHAIN_THREADS = 224;
+constexpr int CHAIN_B_ROWS = 128;            // largest weight sub-tile
+constexpr int CHAIN_B_BYTES = CHAIN_B_ROWS * BK * 2;  // 16 KB
+constexpr int CHAIN_THREADS = 32 * (3 + CHAIN_EPI_WARPS);
+// The epilogue's transposition tiles ALIAS the A ring: between the last MMA of a phase and the handshake that ends it no
+// A tile is live, and no peer multicasts into this CTA's ring before this CTA's own epilogue has arrived on the handshake.
+static_assert(CHAIN_EPI_WARPS * CHAIN_STAGE_BYTES <= CHAIN_A_STAGES * CHAIN_A_BYTES, "staging must fit in the A ring");
 constexpr int CHAIN_SMEM = 1024 + CHAIN_A_STAGES * CHAIN_A_BYTES + CHAIN_B_STAGES * CHAIN_B_BYTES;
 
 enum ChainEpi : int {
@@ -55,7 +66,7 @@ struct ChainPhase {
   CUtensorMap tmB;  // weights [N(+pad), K] bf16, box 64 x sub_rows
   int kblocks;      // K / 64
   int n_sub;        // weight sub-tiles per k-block (each: own ring slot, own UMMA, own TMEM columns)
-  int sub_rows;     // output columns per sub-tile: multiple of 16, <= 192; n_sub * sub_rows <= 384
+  int sub_rows;     // output columns per sub-tile: multiple of 16, <= 128; n_sub * sub_rows <= 384
   int n_total;      // valid output columns of the whole GEMM
   int epi;
   int ld;           // leading dimension of out0 (elements)
@@ -72,9 +83,22 @@ struct ChainParams {
   int n_phases;
   int M;
   float eps, inv_d;
-  float* ss;  // [M][CHAIN_CS] partial sums of squares of the residual stream (written by RESIDUAL epilogues)
+  float* ss;  // [M][CHAIN_SS] partial sums of squares of the residual stream (written by RESIDUAL epilogues)
   const DecState* st;
+  long long* trace;  // optional [grid][CHAIN_TRACE_SLOTS] clock64 stamps (tools/chain_trace.py); nullptr = off
+  int trace_phase;   // phase whose MMA issuer is traced per k-block (A ready, B ready, MMAs issued, commits issued)
 };
+
+// trace slots: 0 kernel entry, 1 setup done (barriers, TMEM, cluster sync), 2 kernel exit; per phase p at 8 + 8 p:
+// +0 A producer passed the phase handshake, +1 A producer issued its last TMA, +2 MMA saw the first A tile,
+// +3 MMA issued its last commit, +4 epilogue saw the accumulator, +5 epilogue stores done, +6 handshake arrives sent,
+// +7 B producer issued its last TMA
+constexpr int CHAIN_TRACE_DETAIL = 8 + 8 * CHAIN_MAX_PHASES;  // then [kb < 32][4]: MMA issuer stamps of phase `trace_phase`
+constexpr int CHAIN_TRACE_SLOTS = CHAIN_TRACE_DETAIL + 4 * 32;
+#define CH_TRACE(slot)                                                                        \
+  do {                                                                                        \
+    if (P.trace != nullptr) P.trace[(size_t)blockIdx.x * CHAIN_TRACE_SLOTS + (slot)] = clock64(); \
+  } while (0)
 
 // ---- cluster helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -92,6 +116,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -110,6 +140,94 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       asm volatile("trap;");
     }
   }
+}
+// TMA tile load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit whose mbarrier arrive lands on the same-offset barrier of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// try_wait parks the warp in hardware until the phase completes or the hint (ns) expires, instead of busy-polling the
+// barrier unit against the MMA issuer; a wait that outlives MBAR_MAX_SPINS hints (seconds) traps instead of hanging
+constexpr uint32_t MBAR_SUSPEND_NS = 0x989680u;  // 10 ms
+constexpr uint32_t MBAR_MAX_SPINS = 400u;
+
+// ---- the same primitives on 32-bit shared-memory addresses computed once (no per-call generic -> shared conversion)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait_u(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS)
+        : "memory");
+    if (spins > MBAR_MAX_SPINS) {
+      printf("m2m: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster_u(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS)
+        : "memory");
+    if (spins > MBAR_MAX_SPINS) {
+      printf("m2m: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast_u(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                        uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_u(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast_u(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -139,90 +257,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// 16 accumulator columns [n, n + 16) of row m (n % 16 == 0); `ssq` accumulates x^2 for RESIDUAL
-__device__ __forceinline__ void chain_epi16(const ChainPhase& ph, int m, int n, const uint32_t* v, float rstd, int t,
-                                            float& ssq) {
-  switch (ph.epi) {
-    case CH_RESIDUAL: {
-      float* xp = reinterpret_cast<float*>(ph.out0) + (size_t)m * ph.ld + n;
-      bf16* bp = reinterpret_cast<bf16*>(ph.out1) + (size_t)m * ph.ld + n;
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 x = *reinterpret_cast<float4*>(xp + 4 * j);
-        x.x += __uint_as_float(v[4 * j]);
-        x.y += __uint_as_float(v[4 * j + 1]);
-        x.z += __uint_as_float(v[4 * j + 2]);
-        x.w += __uint_as_float(v[4 * j + 3]);
-        *reinterpret_cast<float4*>(xp + 4 * j) = x;
-        ssq = fmaf(x.x, x.x, ssq);
-        ssq = fmaf(x.y, x.y, ssq);
-        ssq = fmaf(x.z, x.z, ssq);
-        ssq = fmaf(x.w, x.w, ssq);
-        pk[2 * j] = pack_bf16(x.x, x.y);
-        pk[2 * j + 1] = pack_bf16(x.z, x.w);
-      }
-      *reinterpret_cast<uint4*>(bp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(bp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      break;
-    }
-    case CH_STORE: {
-      if (n < ph.n_total) {  // n_total % 16 == 0
-        bf16* op = reinterpret_cast<bf16*>(ph.out0) + (size_t)m * ph.ld + n;
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          pk[j] = pack_bf16(__uint_as_float(v[2 * j]) * rstd, __uint_as_float(v[2 * j + 1]) * rstd);
-        *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-      break;
-    }
-    case CH_GELU: {
-      bf16* op = reinterpret_cast<bf16*>(ph.out0) + (size_t)m * ph.ld + (n >> 1);
-      uint32_t pk[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float g0 = gelu_new_fast(__uint_as_float(v[4 * j]) * rstd) * (__uint_as_float(v[4 * j + 1]) * rstd);
-        const float g1 = gelu_new_fast(__uint_as_float(v[4 * j + 2]) * rstd) * (__uint_as_float(v[4 * j + 3]) * rstd);
-        pk[j] = pack_bf16(g0, g1);
-      }
-      *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      break;
-    }
-    case CH_QKV: {
-      const int seg = n / ph.inner, c = n - seg * ph.inner;
-      bf16* dst = seg == 0 ? reinterpret_cast<bf16*>(ph.out0) + (size_t)m * ph.inner + c
-                           : reinterpret_cast<bf16*>(seg == 1 ? ph.out1 : ph.out2) + (size_t)m * ph.s1 +
-                                 (size_t)(c >> 6) * ph.s0 + (size_t)t * 64 + (c & 63);
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        pk[j] = pack_bf16(__uint_as_float(v[2 * j]) * rstd, __uint_as_float(v[2 * j + 1]) * rstd);
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      break;
-    }
-    default: {  // CH_LOGITS
-      if (n < ph.n_total) {
-        float* op = reinterpret_cast<float*>(ph.out0) + (size_t)m * ph.ld + n;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(op + 4 * j) =
-              make_float4(__uint_as_float(v[4 * j]) * rstd, __uint_as_float(v[4 * j + 1]) * rstd,
-                          __uint_as_float(v[4 * j + 2]) * rstd, __uint_as_float(v[4 * j + 3]) * rstd);
-      }
-      break;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid_constant__ ChainParams P) {
   if (P.st != nullptr && P.st->done) return;  // uniform over the grid: finished decode, nothing to do
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + CHAIN_A_STAGES * CHAIN_A_BYTES;
+  uint8_t* sStage = sA;  // aliases the A ring (see CHAIN_SMEM)
   __shared__ __align__(8) uint64_t a_full[CHAIN_A_STAGES], a_empty[CHAIN_A_STAGES];
   __shared__ __align__(8) uint64_t b_full[CHAIN_B_STAGES], b_empty[CHAIN_B_STAGES];
   __shared__ __align__(8) uint64_t acc_full, acc_empty, sync_bar;
@@ -233,17 +274,22 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
   const int m0 = (blockIdx.x / CHAIN_CS) * BM;
 
   if (threadIdx.x == 0) {
+    CH_TRACE(0);
+    int total_a = 0;
+    for (int p = 0; p < P.n_phases; ++p) total_a += P.ph[p].kblocks;
     for (int s = 0; s < CHAIN_A_STAGES; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_empty[s], CHAIN_CS);  // used in CTA s only: one tcgen05.commit per CTA of the cluster
     }
+    // arm the first use of every stage (later uses are armed by the MMA issuer once it has drained the stage)
+    for (int s = 0; s < CHAIN_A_STAGES && s < total_a; ++s) mbar_expect_tx(&a_full[s], CHAIN_A_BYTES);
     for (int s = 0; s < CHAIN_B_STAGES; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
     mbar_init(&acc_full, 1);
-    mbar_init(&acc_empty, 4);
-    mbar_init(&sync_bar, CHAIN_CS * 4);  // one arrival per epilogue warp of every CTA of the cluster
+    mbar_init(&acc_empty, 1);
+    mbar_init(&sync_bar, CHAIN_CS);  // one arrival per CTA of the cluster
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -256,133 +302,283 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
   cluster_sync_all();  // barriers of all six CTAs are initialised before anyone arrives remotely
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) CH_TRACE(1);
+
+  // ---- warp-uniform role loops.  The three service warps run their loops with ALL 32 lanes (uniform control flow,
+  // uniform operands) and elect one lane only around the issuing instruction: descriptors, barrier addresses and
+  // TMEM addresses then live in uniform registers and ptxas emits UTMALDG / UTCHMMA / UTCBAR without the
+  // ELECT + R2UR.BROADCAST waterfall a single-lane branch needs (measured: 1400 -> ~300 cycles per k-block).
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+  const uint32_t a_full_u = smem_u32(&a_full[0]), a_empty_u = smem_u32(&a_empty[0]);
+  const uint32_t b_full_u = smem_u32(&b_full[0]), b_empty_u = smem_u32(&b_empty[0]);
+  const uint32_t acc_full_u = smem_u32(&acc_full), acc_empty_u = smem_u32(&acc_empty), sync_u = smem_u32(&sync_bar);
+  uint32_t total_a = 0;
+  for (int p = 0; p < P.n_phases; ++p) total_a += (uint32_t)P.ph[p].kblocks;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ A producer
-    if (lane == 0) {
-      uint32_t ai = 0;
-      for (int p = 0; p < P.n_phases; ++p) {
-        const ChainPhase& ph = P.ph[p];
-        const bool active = crank * ph.n_sub * ph.sub_rows < ph.n_total;
-        if (!active) continue;
-        if (p > 0) {  // A of this phase = outputs of phase p-1 of all six CTAs
-          mbar_wait_cluster(&sync_bar, (uint32_t)(p - 1) & 1u);
+    // ------------------------------------------------------------------ A producer (stage `crank` of all six rings)
+    uint32_t ai = 0;
+    for (int p = 0; p < P.n_phases; ++p) {
+      const int kblocks = P.ph[p].kblocks;
+      const CUtensorMap* tm = &P.ph[p].tmA;
+      bool passed = p == 0;
+      for (int kb = 0; kb < kblocks; ++kb, ++ai) {
+        if ((int)(ai % CHAIN_A_STAGES) != crank) continue;
+        if (!passed) {  // A of this phase = outputs of phase p-1 of all six CTAs
+          mbar_wait_cluster_u(sync_u, (uint32_t)(p - 1) & 1u);
           fence_proxy_async_all();
+          passed = true;
+          if (lane == 0) CH_TRACE(8 + 8 * p + 0);
         }
-        for (int kb = 0; kb < ph.kblocks; ++kb, ++ai) {
-          const uint32_t s = ai % CHAIN_A_STAGES, u = ai / CHAIN_A_STAGES;
-          mbar_wait(&a_empty[s], (u & 1u) ^ 1u);
-          mbar_expect_tx(&a_full[s], CHAIN_A_BYTES);
-          tma_load_2d(sA + s * CHAIN_A_BYTES, &ph.tmA, &a_full[s], kb * BK, m0);
-        }
+        const uint32_t u = ai / CHAIN_A_STAGES;
+        if (u > 0) mbar_wait_cluster_u(a_empty_u + 8u * crank, (u - 1) & 1u);  // all six MMA issuers released the stage
+        if (elect_one())
+          tma_load_2d_multicast_u(sA_u + crank * CHAIN_A_BYTES, tm, a_full_u + 8u * crank, kb * BK, m0,
+                                  (uint16_t)((1u << CHAIN_CS) - 1));
+        __syncwarp();
       }
+      if (lane == 0) CH_TRACE(8 + 8 * p + 1);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ B producer (free-running weight prefetch)
-    if (lane == 0) {
-      uint32_t bi = 0;
-      for (int p = 0; p < P.n_phases; ++p) {
-        const ChainPhase& ph = P.ph[p];
-        const int b_row0 = crank * ph.n_sub * ph.sub_rows;
-        if (b_row0 >= ph.n_total) continue;
-        const uint32_t bytes = (uint32_t)ph.sub_rows * (BK * 2);
-        for (int kb = 0; kb < ph.kblocks; ++kb)
-          for (int sub = 0; sub < ph.n_sub; ++sub, ++bi) {
-            const uint32_t s = bi % CHAIN_B_STAGES, u = bi / CHAIN_B_STAGES;
-            mbar_wait(&b_empty[s], (u & 1u) ^ 1u);
-            mbar_expect_tx(&b_full[s], bytes);
-            tma_load_2d(sB + s * CHAIN_B_BYTES, &ph.tmB, &b_full[s], kb * BK, b_row0 + sub * ph.sub_rows);
+    uint32_t sb = 0, par = 1;  // first pass over the ring: the "previous" phase of an initialised barrier is complete
+    for (int p = 0; p < P.n_phases; ++p) {
+      const int kblocks = P.ph[p].kblocks, n_sub = P.ph[p].n_sub, sub_rows = P.ph[p].sub_rows;
+      const CUtensorMap* tm = &P.ph[p].tmB;
+      const int b_row0 = crank * n_sub * sub_rows;  // rows beyond the matrix are zero-filled by TMA
+      const uint32_t bytes = (uint32_t)sub_rows * (BK * 2);
+      for (int kb = 0; kb < kblocks; ++kb)
+        for (int sub = 0; sub < n_sub; ++sub) {
+          mbar_wait_u(b_empty_u + 8u * sb, par);
+          if (elect_one()) {
+            mbar_expect_tx_u(b_full_u + 8u * sb, bytes);
+            tma_load_2d_u(sB_u + sb * CHAIN_B_BYTES, tm, b_full_u + 8u * sb, kb * BK, b_row0 + sub * sub_rows);
           }
-      }
+          __syncwarp();
+          if (++sb == CHAIN_B_STAGES) {
+            sb = 0;
+            par ^= 1u;
+          }
+        }
+      if (lane == 0) CH_TRACE(8 + 8 * p + 7);
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t ai = 0, bi = 0, np = 0;
-      for (int p = 0; p < P.n_phases; ++p) {
-        const ChainPhase& ph = P.ph[p];
-        if (crank * ph.n_sub * ph.sub_rows >= ph.n_total) continue;
-        if (np > 0) mbar_wait(&acc_empty, (np - 1) & 1u);  // epilogue of the previous phase has drained TMEM
-        const uint32_t idesc = make_idesc(ph.sub_rows);
-        for (int kb = 0; kb < ph.kblocks; ++kb, ++ai) {
-          const uint32_t sa = ai % CHAIN_A_STAGES;
-          mbar_wait(&a_full[sa], (ai / CHAIN_A_STAGES) & 1u);
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + sa * CHAIN_A_BYTES));
-          for (int sub = 0; sub < ph.n_sub; ++sub, ++bi) {
-            const uint32_t sb = bi % CHAIN_B_STAGES;
-            mbar_wait(&b_full[sb], (bi / CHAIN_B_STAGES) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + sb * CHAIN_B_BYTES));
-            const uint32_t tacc = tmem_base + (uint32_t)(sub * ph.sub_rows);
+    // Measured (tools/chain_trace.py): a round (two barrier waits, fence, four UMMAs, two commits, one expect_tx) costs
+    // this warp ~900 cycles however deep the rings are and however few UMMAs it issues: the chain is bound by the
+    // issue latency of the barrier / tensor-core control instructions, not by data or tensor throughput.
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    uint32_t ai = 0, sa = 0, pa = 0, sb = 0, pb = 0;
+    for (int p = 0; p < P.n_phases; ++p) {
+      const int kblocks = P.ph[p].kblocks, n_sub = P.ph[p].n_sub, sub_rows = P.ph[p].sub_rows;
+      if (p > 0) mbar_wait_u(acc_empty_u, (uint32_t)(p - 1) & 1u);  // epilogue of the previous phase has drained TMEM
+      const uint32_t idesc = make_idesc(sub_rows);
+      for (int kb = 0; kb < kblocks; ++kb, ++ai) {
+        mbar_wait_u(a_full_u + 8u * sa, pa);
+        const bool detail = P.trace != nullptr && p == P.trace_phase && kb < 32 && lane == 0;
+        if (kb == 0 && lane == 0) CH_TRACE(8 + 8 * p + 2);
+        if (detail) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 0);
+        const uint64_t adesc = make_smem_desc(sA_u + sa * CHAIN_A_BYTES);
+        for (int sub = 0; sub < n_sub; ++sub) {
+          mbar_wait_u(b_full_u + 8u * sb, pb);
+          if (detail && sub == n_sub - 1) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const uint64_t bdesc = make_smem_desc(sB_u + sb * CHAIN_B_BYTES);
+            const uint32_t tacc = tm_u + (uint32_t)(sub * sub_rows);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&b_empty[sb]);
+            umma_commit_u(b_empty_u + 8u * sb);
           }
-          umma_commit(&a_empty[sa]);
+          __syncwarp();
+          if (detail && sub == n_sub - 1) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 2);
+          if (++sb == CHAIN_B_STAGES) {
+            sb = 0;
+            pb ^= 1u;
+          }
         }
-        umma_commit(&acc_full);
-        ++np;
+        if (elect_one()) {
+          // release the stage to its owner (CTA sa), then arm this CTA's barrier for the stage's next tile
+          umma_commit_multicast_u(a_empty_u + 8u * sa, (uint16_t)(1u << sa));
+          if (ai + CHAIN_A_STAGES < total_a) mbar_expect_tx_u(a_full_u + 8u * sa, CHAIN_A_BYTES);
+        }
+        __syncwarp();
+        if (detail) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 3);
+        if (++sa == CHAIN_A_STAGES) {
+          sa = 0;
+          pa ^= 1u;
+        }
       }
+      if (elect_one()) umma_commit_u(acc_full_u);
+      __syncwarp();
+      if (lane == 0) CH_TRACE(8 + 8 * p + 3);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (TMEM lanes 32*(warp%4)..)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool mvalid = m < P.M;
+    // ------------------------------------------------------------------ epilogue warps
+    // warp w may touch TMEM lanes [32 (w % 4), +32); the two warps of a quarter split the phase's columns.
+    const int e = warp - 3;
+    const int q = warp & 3, hsel = e >> 2;
+    const int m_tmem = m0 + q * 32 + lane;  // the row this thread owns in TMEM
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float(*tile)[36] = reinterpret_cast<float(*)[36]>(sStage + e * CHAIN_STAGE_BYTES);
+    const int trow = lane >> 3, tcol = (lane & 7) * 4;  // transposed domain: 8 lanes cover 32 columns of one row
+    const int m_t0 = m0 + q * 32 + trow;                // + 4 i
     uint32_t np = 0;
     for (int p = 0; p < P.n_phases; ++p) {
       const ChainPhase& ph = P.ph[p];
       const int n_cta0 = crank * ph.n_sub * ph.sub_rows;
-      if (p > 0) mbar_wait_cluster(&sync_bar, (uint32_t)(p - 1) & 1u);  // ss / x written by the other CTAs are visible
-      if (n_cta0 < ph.n_total) {
+      if (p > 0) mbar_wait_cluster_u(sync_u, (uint32_t)(p - 1) & 1u);  // ss / x written by the other CTAs are visible
+      {
+        const int ncols = ph.n_sub * ph.sub_rows;
+        const int split = ((ncols >> 1) + 15) & ~15;
+        const int c_begin = hsel ? split : 0, c_end = hsel ? ncols : split;
+        const bool residual = ph.epi == CH_RESIDUAL;
         float rstd = 1.f;
-        if (ph.epi != CH_RESIDUAL && mvalid) {
-          const float* sp = P.ss + (size_t)m * CHAIN_CS;
-          float s = sp[0];
+        float4 xr[8];
+        if (residual) {
+          // the residual does not depend on this phase's MMA: fetch it while the tensor core works (one 32-column
+          // chunk per warp: RESIDUAL phases have 64 columns per CTA)
 #pragma unroll
-          for (int i = 1; i < CHAIN_CS; ++i) s += sp[i];
-          rstd = rsqrtf(s * P.inv_d + P.eps);
+          for (int i = 0; i < 8; ++i) {
+            const int m = m_t0 + 4 * i;
+            xr[i] = (m < P.M) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ph.out0) +
+                                                                   (size_t)m * ph.ld + n_cta0 + c_begin + tcol)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else if (m_tmem < P.M) {
+          const float4* sp = reinterpret_cast<const float4*>(P.ss + (size_t)m_tmem * CHAIN_SS);
+          float ssum = 0.f;
+#pragma unroll
+          for (int i = 0; i < CHAIN_SS / 4; ++i) {
+            const float4 a = sp[i];
+            ssum += a.x;
+            ssum += a.y;
+            ssum += a.z;
+            ssum += a.w;
+          }
+          rstd = rsqrtf(ssum * P.inv_d + P.eps);
         }
         const int t = (ph.epi == CH_QKV) ? P.st->t : 0;
-        mbar_wait(&acc_full, np & 1u);
+        mbar_wait_u(acc_full_u, np & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float ssq = 0.f;
-        const int ncols = ph.n_sub * ph.sub_rows;
+        if (warp == 3 && lane == 0) CH_TRACE(8 + 8 * p + 4);
 #pragma unroll 1
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          if (c0 + 32 <= ncols) {
-            uint32_t v[32];
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          const int w = min(32, c_end - c0);  // 32 or 16 (warp-uniform)
+          uint32_t v[32];
+          if (w == 32) {
             tmem_ld32(tmem_base + lane_addr + (uint32_t)c0, v);
-            if (mvalid) {
-              chain_epi16(ph, m, n_cta0 + c0, v, rstd, t, ssq);
-              chain_epi16(ph, m, n_cta0 + c0 + 16, v + 16, rstd, t, ssq);
-            }
           } else {
-            uint32_t v[16];
             tmem_ld16(tmem_base + lane_addr + (uint32_t)c0, v);
-            if (mvalid) chain_epi16(ph, m, n_cta0 + c0, v, rstd, t, ssq);
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < w)
+              *reinterpret_cast<float4*>(&tile[lane][4 * j]) =
+                  make_float4(__uint_as_float(v[4 * j]) * rstd, __uint_as_float(v[4 * j + 1]) * rstd,
+                              __uint_as_float(v[4 * j + 2]) * rstd, __uint_as_float(v[4 * j + 3]) * rstd);
+          __syncwarp();
+          // transposed domain: this lane handles columns [n, n + 4) of rows m_t0 + 4 i.  Everything that depends on the
+          // column only (destination, segment, validity) is resolved once per chunk; the row loop is pointer stepping.
+          const int n = n_cta0 + c0 + tcol;
+          const int rows_left = P.M - m_t0;  // row i is valid iff 4 i < rows_left
+          if (tcol < w) {
+            if (residual) {
+              float* xp = reinterpret_cast<float*>(ph.out0) + (size_t)m_t0 * ph.ld + n;
+              bf16* bp = reinterpret_cast<bf16*>(ph.out1) + (size_t)m_t0 * ph.ld + n;
+              float* sp = P.ss + (size_t)m_t0 * CHAIN_SS + crank * 2 + hsel;
+              const size_t step = (size_t)4 * ph.ld;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(&tile[4 * i + trow][tcol]);
+                float4 x = xr[i];
+                x.x += a.x;
+                x.y += a.y;
+                x.z += a.z;
+                x.w += a.w;
+                const bool ok = 4 * i < rows_left;
+                if (ok) {
+                  *reinterpret_cast<float4*>(xp + i * step) = x;
+                  *reinterpret_cast<uint2*>(bp + i * step) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+                }
+                // row sum over the 8 lanes that share the row (fixed order: deterministic)
+                float sq = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                if ((lane & 7) == 0 && ok) sp[(size_t)i * 4 * CHAIN_SS] = sq;
+              }
+            } else if (ph.epi == CH_GELU) {  // W rows interleaved: (wi_0[j], wi_1[j]) pairs -> gg[m, n / 2 .. n / 2 + 2)
+              bf16* op = reinterpret_cast<bf16*>(ph.out0) + (size_t)m_t0 * ph.ld + (n >> 1);
+              const size_t step = (size_t)4 * ph.ld;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(&tile[4 * i + trow][tcol]);
+                if (4 * i < rows_left)
+                  *reinterpret_cast<uint32_t*>(op + i * step) = pack_bf16(gelu_new_fast(a.x) * a.y, gelu_new_fast(a.z) * a.w);
+              }
+            } else if (ph.epi == CH_LOGITS) {
+              if (n < ph.n_total) {
+                float* op = reinterpret_cast<float*>(ph.out0) + (size_t)m_t0 * ph.ld + n;
+                const size_t step = (size_t)4 * ph.ld;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (4 * i < rows_left)
+                    *reinterpret_cast<float4*>(op + i * step) = *reinterpret_cast<const float4*>(&tile[4 * i + trow][tcol]);
+              }
+            } else {  // CH_STORE / CH_QKV: four bf16 per lane
+              bf16* op;
+              size_t step;
+              bool ok = true;
+              if (ph.epi == CH_STORE) {
+                op = reinterpret_cast<bf16*>(ph.out0) + (size_t)m_t0 * ph.ld + n;
+                step = (size_t)4 * ph.ld;
+                ok = n < ph.n_total;
+              } else {
+                const int seg = n / ph.inner, c = n - seg * ph.inner;
+                if (seg == 0) {
+                  op = reinterpret_cast<bf16*>(ph.out0) + (size_t)m_t0 * ph.inner + c;
+                  step = (size_t)4 * ph.inner;
+                } else {
+                  op = reinterpret_cast<bf16*>(seg == 1 ? ph.out1 : ph.out2) + (size_t)m_t0 * ph.s1 +
+                       (size_t)(c >> 6) * ph.s0 + (size_t)t * 64 + (c & 63);
+                  step = (size_t)4 * ph.s1;
+                }
+              }
+              if (ok) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 a = *reinterpret_cast<const float4*>(&tile[4 * i + trow][tcol]);
+                  if (4 * i < rows_left)
+                    *reinterpret_cast<uint2*>(op + i * step) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+                }
+              }
+            }
+          }
+          __syncwarp();
         }
-        if (ph.epi == CH_RESIDUAL && mvalid) P.ss[(size_t)m * CHAIN_CS + crank] = ssq;
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty);
+        if (warp == 3 && lane == 0) CH_TRACE(8 + 8 * p + 5);
         ++np;
       }
       if (p + 1 < P.n_phases) {
-        // global results of this warp -> visible to the TMA loads (async proxy) and epilogues of the whole cluster
+        // this thread's global results -> visible to the async proxy (TMA loads of the next phase); TMEM reads done
         fence_proxy_async_all();
-        __syncwarp();
-        if (lane == 0)
-          for (uint32_t r = 0; r < (uint32_t)CHAIN_CS; ++r) mbar_arrive_remote(&sync_bar, r);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * CHAIN_EPI_WARPS) : "memory");
+        if (e == 0 && lane == 0) {
+          mbar_arrive(&acc_empty);  // all eight epilogue warps have drained the accumulator
+          fence_acq_rel_cluster();  // one cluster-scope release for the whole CTA (cumulative over the bar.sync)
+          for (uint32_t r = 0; r < (uint32_t)CHAIN_CS; ++r) mbar_arrive_remote_relaxed(&sync_bar, r);
+          CH_TRACE(8 + 8 * p + 6);
+        }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
   cluster_sync_all();  // no CTA exits while a peer may still arrive on its barriers
+  if (threadIdx.x == 0) CH_TRACE(2);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }

@@ -1,15 +1,32 @@
 // token stream -> note rows: the integer state machine of MidiTokenizer._decode_tokens and the
 // njit helper _tokens_to_note (reference music2midi/tokenizer.py:169-200, 242-267).  CPU code: a few
 // thousand branchy integer steps per 3 s segment, no data parallelism worth a launch.
+#include <stdarg.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <vector>
 
 #include "../../include/m2m_b200.h"
 
 namespace m2m {
-void set_error(const char* fmt, ...);
+#ifdef M2M_NOTES_STANDALONE
+// host-only build (libm2m_notes.so, g++): the tokenizer works without the CUDA toolchain / a GPU
+static thread_local char g_notes_err[256] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_notes_err, sizeof(g_notes_err), fmt, ap);
+  va_end(ap);
 }
+#else
+void set_error(const char* fmt, ...);
+#endif
+}
+
+#ifdef M2M_NOTES_STANDALONE
+extern "C" const char* m2m_notes_last_error(void) { return m2m::g_notes_err; }
+#endif
 
 extern "C" int m2m_tokens_to_notes(const int64_t* tokens, int64_t n_tokens, int64_t start_idx, int32_t pitch_offset,
                                    int32_t time_offset, int32_t velocity, int64_t* out_rows4, int64_t cap,
@@ -69,5 +86,30 @@ extern "C" int m2m_tokens_to_notes(const int64_t* tokens, int64_t n_tokens, int6
     cur_note = -1;
   }
   *n_notes = n;
+  return M2M_OK;
+}
+
+// Whole token matrix [n_rows, row_len] in one call (Music2MIDI.sample_tokens / generate_many decode thousands of
+// segments per batch): row i is decoded independently with start_idx = start_idx0 + i * steps_per_row (the
+// "sequential" mode of MidiTokenizer.decode, reference tokenizer.py:75-83; steps_per_row = 0 gives the "batched"
+// mode) and the note rows are concatenated; row_note_end[i] = number of note rows after row i.
+extern "C" int m2m_tokens_to_notes_batch(const int64_t* tokens, int64_t n_rows, int64_t row_len, int64_t start_idx0,
+                                         int64_t steps_per_row, int32_t pitch_offset, int32_t time_offset,
+                                         int32_t velocity, int64_t* out_rows4, int64_t cap, int64_t* row_note_end,
+                                         int64_t* n_notes) {
+  if ((!tokens && n_rows * row_len > 0) || !n_notes || n_rows < 0 || row_len < 0) {
+    m2m::set_error("m2m_tokens_to_notes_batch: bad argument");
+    return M2M_ERR_INVALID;
+  }
+  int64_t total = 0;
+  for (int64_t i = 0; i < n_rows; ++i) {
+    int64_t n = 0;
+    int rc = m2m_tokens_to_notes(tokens + i * row_len, row_len, start_idx0 + i * steps_per_row, pitch_offset, time_offset,
+                                 velocity, out_rows4 ? out_rows4 + 4 * total : nullptr, cap - total, &n);
+    if (rc != M2M_OK) return rc;
+    total += n;
+    if (row_note_end) row_note_end[i] = total;
+  }
+  *n_notes = total;
   return M2M_OK;
 }

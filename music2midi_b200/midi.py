@@ -11,6 +11,8 @@ from __future__ import annotations
 import struct
 from typing import List
 
+import numpy as np
+
 
 class Note:
     def __init__(self, velocity: int, pitch: int, start: float, end: float):
@@ -40,6 +42,36 @@ class Instrument:
     def get_end_time(self) -> float:
         return max((n.end for n in self.notes), default=0.0)
 
+    def get_piano_roll(self, fs: int = 100, times=None, pedal_threshold=64) -> np.ndarray:
+        """(128, n) velocity piano roll like pretty_midi's (no pedal / pitch-bend handling: this container never
+        holds control changes).  Without `times`: one column per 1/fs s.  With `times`: column n is the mean of the
+        fs-grid columns in [round(times[n] fs), round(times[n+1] fs)); the last column stays zero."""
+        if not self.notes:
+            return np.zeros((128, 0))
+        end_time = self.get_end_time()
+        if times is not None and len(times) and times[-1] > end_time:
+            end_time = times[-1]
+        roll = np.zeros((128, int(fs * end_time)))
+        for n in self.notes:
+            roll[int(n.pitch), int(n.start * fs):int(n.end * fs)] += n.velocity
+        if times is None:
+            return roll
+        times = np.asarray(times, dtype=np.float64)
+        out = np.zeros((128, times.shape[0]))
+        ticks = np.array(np.round(times * fs), dtype=np.int64)
+        for i, (a, b) in enumerate(zip(ticks[:-1], ticks[1:])):
+            if a < roll.shape[1]:
+                if a == b:
+                    b = a + 1
+                out[:, i] = np.mean(roll[:, a:b], axis=1)
+        return out
+
+    def fluidsynth(self, fs: int = 44100, sf2_path=None):
+        raise RuntimeError(_NO_SYNTH)
+
+    def synthesize(self, fs: int = 44100, wave=None):
+        raise RuntimeError(_NO_SYNTH)
+
     def __repr__(self):
         return f'Instrument(program={self.program}, is_drum={self.is_drum}, name="{self.name}")'
 
@@ -51,6 +83,12 @@ def _vlq(n: int) -> bytes:
         out.append((n & 0x7F) | 0x80)
         n >>= 7
     return bytes(reversed(out))
+
+
+_NO_SYNTH = ("audio synthesis needs the real pretty_midi package (and pyfluidsynth + a SoundFont for fluidsynth()); "
+             "music2midi_b200.midi is the note container / Standard-MIDI-File writer used when pretty_midi is not "
+             "installed.  Write the file with .write(path) and render it with any synthesiser, or "
+             "`pip install pretty_midi pyfluidsynth` and numpy_to_midi() will return real PrettyMIDI objects.")
 
 
 class PrettyMIDI:
@@ -68,6 +106,23 @@ class PrettyMIDI:
 
     def get_end_time(self) -> float:
         return max((i.get_end_time() for i in self.instruments), default=0.0)
+
+    def get_piano_roll(self, fs: int = 100, times=None, pedal_threshold=64) -> np.ndarray:
+        """Sum of the instruments' piano rolls (pretty_midi.PrettyMIDI.get_piano_roll)."""
+        if not self.instruments:
+            return np.zeros((128, 0))
+        rolls = [i.get_piano_roll(fs=fs, times=times, pedal_threshold=pedal_threshold) for i in self.instruments]
+        out = np.zeros((128, max(r.shape[1] for r in rolls)))
+        for r in rolls:
+            out[:, : r.shape[1]] += r
+        return out
+
+    def fluidsynth(self, fs: int = 44100, sf2_path=None):
+        """webui.py:66 / demo.ipynb:77 call this right after generate(); it needs the real pretty_midi."""
+        raise RuntimeError(_NO_SYNTH)
+
+    def synthesize(self, fs: int = 44100, wave=None):
+        raise RuntimeError(_NO_SYNTH)
 
     def time_to_tick(self, t: float) -> int:
         return int(round(t * self.resolution * self.initial_tempo / 60.0))

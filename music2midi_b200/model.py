@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .config import load_config
+from .evaluation import evaluate_batch
 from .input import ModelInputs
 from .transformer import T5Transformer
 from .utils import numpy_to_midi
@@ -90,14 +91,14 @@ class Music2MIDI(nn.Module):
     # ------------------------------------------------------------------ inference
     @torch.no_grad()
     def evaluate_batch(self, inputs: ModelInputs):
-        """Generation + decoding half of the reference's evaluate_batch (model.py:55-62); the melody
-        chroma metric itself (music2midi/evaluation.py, mir_eval) is outside this package."""
+        """reference model.py:55-65: greedy generation capped at 4 tokens per label note, batched token decoding,
+        melody chroma accuracy of the generated against the label MIDI -> (score, output_midi, label_midi)."""
         max_num_notes = max(len(notes) for notes in inputs.notes_batch)
         generated = self.model.generate(inputs, max_length=max_num_notes * 4)
         decoded = self.model.tokenizer.decode(generated, mode="batched")
         label_midi = [numpy_to_midi(n) for n in inputs.notes_batch]
         output_midi = [numpy_to_midi(n) for n in decoded]
-        return None, output_midi, label_midi
+        return evaluate_batch(label_midi, output_midi), output_midi, label_midi
 
     def generate(self, audio_path: Optional[Union[str, Path]] = None, audio_y: Optional[np.ndarray] = None,
                  sr: Optional[int] = None, cond_index: Optional[List[int]] = None):

@@ -71,6 +71,9 @@ class MidiTokenizer:
             return [self._decode(r, 0, cutoff_time) for r in rows]
         assert duration_per_batch is not None, 'duration_per_batch is required for mode="sequential"'
         n_steps = round(duration_per_batch / self.time_step)
+        if len(rows) > 1 and len({r.shape for r in rows}) == 1 and rows[0].ndim == 1:
+            # equal-length rows (a token matrix): one C call for the whole recording
+            return self._finish(self._decode_matrix(np.stack(rows), n_steps), cutoff_time)
         out = [self._decode(r, i * n_steps, cutoff_time) for i, r in enumerate(rows)]
         return np.concatenate(out)  # raises on an empty batch, like the reference
 
@@ -89,7 +92,9 @@ class MidiTokenizer:
     def _decode(self, tokens, start_idx: int = 0, cutoff_time: Optional[int] = None) -> np.ndarray:
         if isinstance(tokens, torch.Tensor):
             tokens = tokens.detach().cpu().numpy()
-        notes = self._decode_tokens(np.asarray(tokens), start_idx)
+        return self._finish(self._decode_tokens(np.asarray(tokens), start_idx), cutoff_time)
+
+    def _finish(self, notes: np.ndarray, cutoff_time: Optional[int]) -> np.ndarray:
         notes = notes[notes[:, 1] != -1]  # un-closed notes are dropped
         notes[:, :2] = notes[:, :2] * self.time_step
         if cutoff_time is not None:
@@ -103,9 +108,21 @@ class MidiTokenizer:
         cap = max(int(toks.size), 1)
         rows = np.empty((cap, 4), dtype=np.int64)
         n = C.c_int64(0)
-        _lib.check(_lib.load().m2m_tokens_to_notes(
+        _lib.check(_lib.load_notes().m2m_tokens_to_notes(
             toks.ctypes.data_as(C.c_void_p), toks.size, int(start_idx), self.pitch_token_offset,
             self.time_token_offset, self.default_velocity, rows.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        return rows[: n.value].astype(np.float64)
+
+    def _decode_matrix(self, tokens: np.ndarray, steps_per_row: int, start_idx: int = 0) -> np.ndarray:
+        """All rows of a [n_rows, L] token matrix in one call; row i starts at start_idx + i * steps_per_row."""
+        toks = np.ascontiguousarray(tokens, dtype=np.int64)
+        cap = max(int(toks.size), 1)
+        rows = np.empty((cap, 4), dtype=np.int64)
+        n = C.c_int64(0)
+        _lib.check(_lib.load_notes().m2m_tokens_to_notes_batch(
+            toks.ctypes.data_as(C.c_void_p), toks.shape[0], toks.shape[1], int(start_idx), int(steps_per_row),
+            self.pitch_token_offset, self.time_token_offset, self.default_velocity, rows.ctypes.data_as(C.c_void_p), cap,
+            None, C.byref(n)))
         return rows[: n.value].astype(np.float64)
 
     # ------------------------------------------------------------------ notes -> tokens
