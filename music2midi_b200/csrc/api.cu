@@ -121,13 +121,14 @@ struct m2m_ctx {
   bf16* lm_head_ln = nullptr;
   float *window = nullptr, *dft_basis = nullptr, *band_w = nullptr, *cond_emb = nullptr;
   int *band_start = nullptr, *band_len = nullptr, *cond_off = nullptr, *cond_rows = nullptr;
-  int n_freq = 0, dft_rows = 0, max_band = 32, enc_bias_ld = 0;
-  bf16* dft_basis3 = nullptr;  // [3][basis_split_rows][n_fft] bf16: hi/mid/lo terms of the DFT basis (tcgen05 path)
-  int basis_split_rows = 0;
+  int n_freq = 0, max_band = 32, enc_bias_ld = 0;
+  // folded DFT tables [n_fft/2 frequencies][n_fft/2 samples n = 1..n_fft/2]: fp32 cos | sin (dft_basis = cos,
+  // dft_basis + H*H = sin) and their hi/mid/lo bf16 terms [3][H][H] for the tcgen05 path
+  bf16 *dft_cos3 = nullptr, *dft_sin3 = nullptr;
 
   // workspaces
   int64_t generation = 0;
-  DevBuf mel_power, mel_a3, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
+  DevBuf mel_power, mel_a3, mel_y0, embeds, enc_x, enc_h, enc_qkv, enc_ao, enc_g, enc_out;
   DevBuf ckv, skv;  // cross / self KV caches, all layers
   DevBuf dec_xb, dec_x, dec_h, dec_q, dec_ao, dec_g, dec_logits, dec_finished, dec_tokens, dec_state, dec_err, dec_ss;
   DevBuf chain_trace;  // M2M_CHAIN_TRACE=1: clock64 stamps of four chain launches per step (K0, KB[0], KA[0], KA[last])
@@ -270,10 +271,12 @@ static int seq_attn(m2m_ctx* c, const T* Q, int ldq, const T* K, const T* V, siz
 }
 
 // ------------------------------------------------------------------ log-mel
-// Two data paths for the DFT (both followed by the banded mel + clamp + log kernel):
-//   tcgen05: frame_split_kernel (frames x window -> 3 bf16 terms, L2-resident slab) -> gemm_tc_kernel<NSPLIT=3>
-//            (six bf16 products into one fp32 TMEM accumulator, EpiPower epilogue)
-//   fp32   : gemm_simt_kernel<FrameA, EpiPower> (frames built on the fly, FFMA)
+// The DFT is evaluated as TWO half-size GEMMs on the even / odd halves of the windowed frame (real-input symmetry, see
+// fold_split_kernel): Re X = y[0] + E . cos^T, Im X = - O . sin^T, K = N = n_fft / 2 each - half the multiply-adds of
+// the plain [frames x n_fft] . [n_fft x 2 n_freq] product.  Two data paths, both followed by the banded mel kernel:
+//   tcgen05: fold_split_kernel (E and O as 3 bf16 terms each, L2-resident slab) -> 2 x gemm_tc_kernel<NSPLIT=3>
+//            (six bf16 products per fp32 product into one fp32 TMEM accumulator; EpiDftRe, then EpiDftPower)
+//   fp32   : 2 x gemm_simt_kernel<FoldA, ...> (halves built on the fly, FFMA)
 static bool mel_use_tc(const m2m_ctx* c) {
   if (c->flags & 16u) return false;
   if (c->flags & 32u) return true;
@@ -285,34 +288,56 @@ static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_m
   M2M_REQUIRE(B >= 0 && S > g.n_fft / 2, "logmel: need S > n_fft/2 = %d for reflect padding (got S=%d)", g.n_fft / 2, S);
   if (B == 0) return 0;
   const int T = 1 + S / g.hop;
+  const int H = g.n_fft / 2;
   const size_t M = (size_t)B * T;
   M2M_REQUIRE(M < (1u << 30), "logmel: too many frames (%zu)", M);
   const int ldp = (int)align_up(c->n_freq, 4);
-  const bool use_tc = mel_use_tc(c) && g.n_fft % tc::BK == 0;
+  const bool use_tc = mel_use_tc(c) && H % tc::BK == 0;
   // frames are processed in slabs so that the intermediates stay L2-resident between the kernels
-  const size_t slab_rows = use_tc ? 4096 : 16384;  // tc: 3 x 4096 x 2048 bf16 = 50 MB (+17 MB power) < 126 MB L2
-  M2M_TRY(c->mel_power.ensure(std::min(M, slab_rows) * ldp * sizeof(float), &c->generation));
-  if (use_tc) M2M_TRY(c->mel_a3.ensure(3 * slab_rows * g.n_fft * sizeof(bf16), &c->generation));
+  // tc: 128-row x 128-column tiles, one CTA per SM: a slab of 37 x 128 rows gives 37 x 8 = 296 = 2 x 148 tiles (two
+  // full waves on 148 SMs); 6 x 4736 x 1024 bf16 = 58 MB of operands + 39 MB of Re / Im stay L2-resident (126 MB)
+  const size_t slab_rows = use_tc ? (size_t)(c->num_sms / 4) * 128 : 16384;
+  M2M_TRY(c->mel_power.ensure(2 * std::min(M, slab_rows) * ldp * sizeof(float), &c->generation));
+  M2M_TRY(c->mel_y0.ensure(std::min(M, slab_rows) * sizeof(float), &c->generation));
+  if (use_tc) M2M_TRY(c->mel_a3.ensure(6 * slab_rows * H * sizeof(bf16), &c->generation));
+  float* Re = c->mel_power.as<float>();
+  float* Im = Re + std::min(M, slab_rows) * ldp;
+  float* y0 = c->mel_y0.as<float>();
   for (size_t r0 = 0; r0 < M; r0 += slab_rows) {
     size_t rows = std::min(slab_rows, M - r0);
-    EpiPower epi{c->mel_power.as<float>(), ldp, c->n_freq};
     cudaError_t e;
     if (use_tc) {
+      bf16* E3 = c->mel_a3.as<bf16>();
+      bf16* O3 = E3 + 3 * slab_rows * H;
       {
         TimedScope ts(c, KC_MEL_FRAME, s);
-        size_t total = rows * (size_t)(g.n_fft / 8);
-        unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16);
-        frame_split_kernel<<<blocks, 256, 0, s>>>(d_wave, c->window, c->mel_a3.as<bf16>(), S, T, g.hop, g.n_fft, (int)r0,
-                                                  (int)rows, slab_rows * g.n_fft);
+        unsigned blocks = (unsigned)std::min<size_t>((rows + 7) / 8, (size_t)c->num_sms * 8);
+        fold_split_kernel<<<blocks, 256, 0, s>>>(d_wave, c->window, E3, O3, y0, Re, Im, ldp, S, T, g.hop, g.n_fft, (int)r0,
+                                                 (int)rows, slab_rows * H);
         LAUNCH_CHECK(c);
       }
       TimedScope ts(c, KC_MEL_DFT, s);
-      e = tc::launch_cfg<128, 2, EpiPower, 3>(c->mel_a3.as<bf16>(), g.n_fft, c->dft_basis3, (int)rows, c->dft_rows,
-                                              g.n_fft, epi, nullptr, s, (int)slab_rows, c->basis_split_rows);
+      e = tc::launch_cfg<128, 2, EpiDftRe, 3>(E3, H, c->dft_cos3, (int)rows, H, H, EpiDftRe{Re, y0, ldp}, nullptr, s,
+                                              (int)slab_rows, H);
+      if (e == cudaSuccess)
+        e = tc::launch_cfg<128, 2, EpiStore<float>, 3>(O3, H, c->dft_sin3, (int)rows, H, H, EpiStore<float>{Im, ldp}, nullptr,
+                                                       s, (int)slab_rows, H);
+      c->stats.kernel_launches++;
     } else {
+      {
+        TimedScope ts(c, KC_MEL_FRAME, s);
+        unsigned blocks = (unsigned)std::min<size_t>((rows + 255) / 256, (size_t)c->num_sms * 8);
+        dft_edge_kernel<<<blocks, 256, 0, s>>>(d_wave, c->window, y0, Re, Im, ldp, S, T, g.hop, g.n_fft, (int)r0, (int)rows);
+        LAUNCH_CHECK(c);
+      }
       TimedScope ts(c, KC_MEL_DFT, s);
-      FrameA a{d_wave, c->window, S, T, g.hop, g.n_fft / 2, (int)r0};
-      e = launch_gemm_simt(a, c->dft_basis, g.n_fft, (int)rows, c->dft_rows, g.n_fft, epi, nullptr, s, c->num_sms);
+      FoldA a{d_wave, c->window, S, T, g.hop, g.n_fft, (int)r0, 0};
+      e = launch_gemm_simt(a, c->dft_basis, H, (int)rows, H, H, EpiDftRe{Re, y0, ldp}, nullptr, s, c->num_sms);
+      a.odd = 1;
+      if (e == cudaSuccess)
+        e = launch_gemm_simt(a, c->dft_basis + (size_t)H * H, H, (int)rows, H, H, EpiStore<float>{Im, ldp}, nullptr, s,
+                             c->num_sms);
+      c->stats.kernel_launches++;
     }
     if (e != cudaSuccess) {
       set_error("logmel DFT launch failed: %s", cudaGetErrorString(e));
@@ -322,10 +347,9 @@ static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_m
     M2M_REQUIRE(g.d_model <= 512, "mel_band_log: n_mels %d > 512 is not supported", g.d_model);
     TimedScope ts(c, KC_MEL_BAND, s);
     const unsigned bthreads = (unsigned)((g.d_model + 31) / 32 * 32);
-    const unsigned bblocks = (unsigned)std::min<size_t>(rows, (size_t)c->num_sms * 5);
-    mel_band_log_kernel<<<bblocks, bthreads, 2 * (size_t)ldp * sizeof(float), s>>>(
-        c->mel_power.as<float>(), ldp, c->band_start, c->band_len, c->band_w, c->max_band, d_mel + r0 * g.d_model, rows,
-        g.d_model);
+    const unsigned bblocks = (unsigned)std::min<size_t>((rows + MEL_ROWS - 1) / MEL_ROWS, (size_t)c->num_sms * 4);
+    mel_band_log_kernel<<<bblocks, bthreads, MEL_ROWS * (size_t)ldp * sizeof(float), s>>>(
+        Re, Im, ldp, c->band_start, c->band_len, c->band_w, c->max_band, d_mel + r0 * g.d_model, rows, g.d_model);
     LAUNCH_CHECK(c);
   }
   return 0;
@@ -1089,7 +1113,7 @@ int m2m_ctx_destroy(m2m_ctx* c) {
   cudaDeviceSynchronize();
   if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
-  DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
+  DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->mel_y0, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
                     &c->enc_out, &c->ckv, &c->skv, &c->dec_xb, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
                     &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->dec_ss, &c->chain_trace, &c->tf_x, &c->tf_h,
                     &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave[0], &c->host_wave[1], &c->host_cond[0],
@@ -1266,9 +1290,10 @@ int m2m_finalize_weights(m2m_ctx* c) {
 
   }  // has_model
 
-  // DFT basis, rows interleaved (2f = cos, 2f+1 = sin), exact integer angle reduction, fp64 -> fp32
-  const int dft_rows = (int)align_up((size_t)2 * n_freq, 4);
-  std::vector<float> basis((size_t)dft_rows * g.n_fft, 0.f);
+  // folded DFT tables: row f = 0..H-1, column k <-> sample n = k + 1 (n = 1..H); exact integer angle reduction
+  // (f n mod N), fp64 -> fp32, plus the hi / mid / lo bf16 terms of the fp64 value for the tcgen05 path
+  const int Hh = g.n_fft / 2;
+  size_t o_basis = 0, o_cos3 = 0, o_sin3 = 0;
   {
     std::vector<double> ct(g.n_fft), stb(g.n_fft);
     for (int r = 0; r < g.n_fft; ++r) {
@@ -1276,47 +1301,30 @@ int m2m_finalize_weights(m2m_ctx* c) {
       ct[r] = cos(a);
       stb[r] = sin(a);
     }
-    for (int f = 0; f < n_freq; ++f)
-      for (int k = 0; k < g.n_fft; ++k) {
-        int r = (int)(((long long)f * k) % g.n_fft);
-        basis[(size_t)(2 * f) * g.n_fft + k] = (float)ct[r];
-        basis[(size_t)(2 * f + 1) * g.n_fft + k] = (float)stb[r];
-      }
-  }
-  size_t o_basis = ab.push_f32(basis);
-  basis.clear();
-  basis.shrink_to_fit();
-  // the same basis as three bf16 terms (hi + mid + lo of the fp64 value), each term padded to a multiple of the
-  // 128-row tile, stacked [3][basis_split_rows][n_fft] for the tcgen05 path
-  const int basis_split_rows = (int)align_up((size_t)dft_rows, 128);
-  size_t o_basis3 = 0;
-  {
-    std::vector<uint16_t> b3((size_t)3 * basis_split_rows * g.n_fft, 0);
-    std::vector<double> ct(g.n_fft), stb(g.n_fft);
-    for (int r = 0; r < g.n_fft; ++r) {
-      double ang = 2.0 * M_PI * (double)r / (double)g.n_fft;
-      ct[r] = cos(ang);
-      stb[r] = sin(ang);
-    }
     auto bf2d = [](uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return (double)f; };
-    const size_t term = (size_t)basis_split_rows * g.n_fft;
-    for (int row = 0; row < 2 * n_freq; ++row) {
-      const int f = row >> 1;
-      for (int k = 0; k < g.n_fft; ++k) {
-        int r = (int)(((long long)f * k) % g.n_fft);
-        double x = (row & 1) ? stb[r] : ct[r];
-        uint16_t hi = f2bf((float)x);
-        double r1 = x - bf2d(hi);
-        uint16_t mid = f2bf((float)r1);
-        double r2 = r1 - bf2d(mid);
-        uint16_t lo = f2bf((float)r2);
-        size_t idx = (size_t)row * g.n_fft + k;
-        b3[idx] = hi;
-        b3[term + idx] = mid;
-        b3[2 * term + idx] = lo;
+    const size_t term = (size_t)Hh * Hh;
+    std::vector<float> basis(2 * term);
+    std::vector<uint16_t> c3(3 * term), s3(3 * term);
+    for (int f = 0; f < Hh; ++f)
+      for (int k = 0; k < Hh; ++k) {
+        const int r = (int)(((long long)f * (k + 1)) % g.n_fft);
+        const size_t idx = (size_t)f * Hh + k;
+        for (int which = 0; which < 2; ++which) {
+          const double x = which ? stb[r] : ct[r];
+          basis[which * term + idx] = (float)x;
+          std::vector<uint16_t>& dst = which ? s3 : c3;
+          uint16_t hi = f2bf((float)x);
+          double r1 = x - bf2d(hi);
+          uint16_t mid = f2bf((float)r1);
+          double r2 = r1 - bf2d(mid);
+          dst[idx] = hi;
+          dst[term + idx] = mid;
+          dst[2 * term + idx] = f2bf((float)r2);
+        }
       }
-    }
-    o_basis3 = ab.push_bytes(b3.data(), b3.size() * 2);
+    o_basis = ab.push_f32(basis);
+    o_cos3 = ab.push_bytes(c3.data(), c3.size() * 2);
+    o_sin3 = ab.push_bytes(s3.data(), s3.size() * 2);
   }
 
   // banded mel filterbank
@@ -1384,9 +1392,8 @@ int m2m_finalize_weights(m2m_ctx* c) {
   c->dec_bias = F32(o_decb);
   c->dec_bias_seq = F32(o_decbs);
   c->dft_basis = F32(o_basis);
-  c->dft_basis3 = reinterpret_cast<bf16*>(base + o_basis3);
-  c->basis_split_rows = basis_split_rows;
-  c->dft_rows = dft_rows;
+  c->dft_cos3 = reinterpret_cast<bf16*>(base + o_cos3);
+  c->dft_sin3 = reinterpret_cast<bf16*>(base + o_sin3);
   c->n_freq = n_freq;
   c->band_start = reinterpret_cast<int*>(base + o_bs);
   c->band_len = reinterpret_cast<int*>(base + o_bl);

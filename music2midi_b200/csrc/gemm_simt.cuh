@@ -22,24 +22,32 @@ struct RowMajorA {
   __device__ __forceinline__ void load4(int m, int k, float o[4]) const { m2m::load4(A + (size_t)m * lda + k, o); }
 };
 
-// Frames of the STFT built on the fly from the waveform: row m = (b, t), column k = sample n of the
-// frame: wave[b][reflect(t*hop + n - n_fft/2)] * window[n].   (torch.stft center=True, reflect)
-struct FrameA {
+// Even / odd halves of the windowed STFT frames built on the fly from the waveform (see fold_split_kernel): row
+// m = (b, t), column k <-> n = k + 1:  e = y[n] + y[N-n],  o = y[n] - y[N-n]  (n < N/2);  e = y[N/2], o = 0 at n = N/2,
+// with y[n] = wave[b][reflect(t*hop + n - N/2)] * window[n]   (torch.stft center=True, reflect).
+struct FoldA {
   const float* wave;    // [B, S]
   const float* window;  // [n_fft]
-  int S, T, hop, half;
+  int S, T, hop, n_fft;
   int m_off;  // first global frame row of this launch (slabbed launches)
+  int odd;    // 0: even half (cos products), 1: odd half (sin products)
+  __device__ __forceinline__ float sample(const float* w, int base, int n) const {
+    int i = base + n;
+    i = i < 0 ? -i : i;
+    i = i >= S ? 2 * (S - 1) - i : i;
+    return __ldg(w + i) * __ldg(window + n);
+  }
   __device__ __forceinline__ void load4(int m, int k, float o[4]) const {
     m += m_off;
-    int b = m / T, t = m - b * T;
+    const int b = m / T, t = m - b * T;
     const float* w = wave + (size_t)b * S;
-    int base = t * hop + k - half;
+    const int H = n_fft >> 1, base = t * hop - H;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      int i = base + e;
-      i = i < 0 ? -i : i;
-      i = i >= S ? 2 * (S - 1) - i : i;
-      o[e] = __ldg(w + i) * __ldg(window + k + e);
+      const int n = k + 1 + e;
+      const float a = sample(w, base, n);
+      const float bb = n < H ? sample(w, base, n_fft - n) : 0.f;
+      o[e] = odd ? (n < H ? a - bb : 0.f) : a + bb;
     }
   }
 };
@@ -121,15 +129,14 @@ struct EpiHeadMajorKV {
     store4(dst, val);
   }
 };
-// DFT power: W rows interleaved (2f = cos_f, 2f+1 = sin_f):  P[m, f] = re^2 + im^2
-struct EpiPower {
+// Folded DFT, even half x cos table:  Re[m, f] = y0[m] + acc  (the odd half x sin table is a plain EpiStore<float>)
+struct EpiDftRe {
   float* P;
-  int ldp, n_freq;
+  const float* y0;
+  int ldp;
   __device__ __forceinline__ void operator()(int m, int n, const float v[4], const DecState*) const {
-    int f = n >> 1;
-    float* p = P + (size_t)m * ldp + f;
-    if (f < n_freq) p[0] = v[0] * v[0] + v[1] * v[1];
-    if (f + 1 < n_freq) p[1] = v[2] * v[2] + v[3] * v[3];
+    const float a = y0[m];
+    *reinterpret_cast<float4*>(P + (size_t)m * ldp + n) = make_float4(v[0] + a, v[1] + a, v[2] + a, v[3] + a);
   }
 };
 

@@ -474,66 +474,128 @@ __global__ void step_advance_kernel(DecState* st, int greedy_stop) {
   st->unfinished = 0;
 }
 
-// ------------------------------------------------------------------ framing + window + 3-way bf16 split (a3)
-// A3[s][m][n] for s = hi, mid, lo: frame m = (b, t), sample n:  x = wave[b][reflect(t*hop + n - n_fft/2)] * w[n],
-// hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid).  Pure streaming kernel: 16-byte loads of the
-// window, 8 outputs per thread per term written as one 16-byte store; the waveform (reused by n_fft/hop = 8
-// overlapping frames) comes from L1/L2.  `rows` frames starting at global frame `m_off`.
-__global__ void __launch_bounds__(256) frame_split_kernel(const float* __restrict__ wave, const float* __restrict__ window,
-                                                          bf16* __restrict__ A3, int S, int T, int hop, int n_fft,
-                                                          int m_off, int rows, size_t split_stride) {
-  const int chunks = n_fft / 8;
-  const size_t total = (size_t)rows * chunks;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / chunks), ch = (int)(i - (size_t)r * chunks);
+// ------------------------------------------------------------------ framing + window + even/odd fold + 3-way bf16 split (a3)
+// Real-input symmetry of the DFT: with y[n] = wave[b][reflect(t*hop + n - N/2)] * w[n] (frame m = (b, t)) and H = N/2,
+//   Re X[f] = y[0] + sum_{n=1..H} e[n] cos(2 pi f n / N),   e[n] = y[n] + y[N-n]  (n < H),  e[H] = y[H]
+//   Im X[f] =      - sum_{n=1..H} o[n] sin(2 pi f n / N),   o[n] = y[n] - y[N-n]  (n < H),  o[H] = 0
+// so cos and sin each contract over K = H instead of N: half the MMA work of the plain DFT-as-GEMM at identical
+// accuracy.  This kernel writes E and O (column k = n - 1) as three bf16 terms each (x = hi + mid + lo, 24 mantissa
+// bits: the tcgen05 GEMM then accumulates the six significant products in fp32), y[0] per frame (added by the GEMM
+// epilogue) and the Nyquist bin  X[H] = sum_n (-1)^n y[n]  (real) directly into the Re / Im spectrum buffers.
+// One warp per frame: coalesced 16-byte window loads, mirrored waveform reads from L1/L2 (frames overlap 8x).
+__global__ void __launch_bounds__(256) fold_split_kernel(const float* __restrict__ wave, const float* __restrict__ window,
+                                                         bf16* __restrict__ E3, bf16* __restrict__ O3,
+                                                         float* __restrict__ y0, float* __restrict__ Re,
+                                                         float* __restrict__ Im, int ldp, int S, int T, int hop,
+                                                         int n_fft, int m_off, int rows, size_t split_stride) {
+  const int H = n_fft / 2;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
     const int m = m_off + r;
     const int b = m / T, t = m - b * T;
     const float* w = wave + (size_t)b * S;
-    const int n0 = ch * 8;
-    const int base = t * hop + n0 - n_fft / 2;
-    float x[8], wv[8];
-    load4(window + n0, wv);
-    load4(window + n0 + 4, wv + 4);
-    if (base >= 0 && base + 7 < S && (reinterpret_cast<uintptr_t>(w + base) & 15) == 0) {
-      load4(w + base, x);
-      load4(w + base + 4, x + 4);
-    } else {
+    const int base = t * hop - H;  // sample index of n = 0
+    auto sample = [&](int n) -> float {
+      int j = base + n;
+      j = j < 0 ? -j : j;
+      j = j >= S ? 2 * (S - 1) - j : j;
+      return __ldg(w + j) * __ldg(window + n);
+    };
+    float nyq = 0.f;  // sum over the pairs (n, N - n) handled by this lane of (-1)^n (y[n] + y[N-n])
+    bf16* erow = E3 + (size_t)r * H;
+    bf16* orow = O3 + (size_t)r * H;
+    for (int k0 = lane * 8; k0 < H; k0 += 32 * 8) {  // columns k0 .. k0+7  <->  n = k0+1 .. k0+8
+      float e[8], o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        int j = base + e;
-        j = j < 0 ? -j : j;
-        j = j >= S ? 2 * (S - 1) - j : j;
-        x[e] = __ldg(w + j);
+      for (int i = 0; i < 8; ++i) {
+        const int n = k0 + 1 + i;
+        const float a = sample(n);
+        const float bb = (n < H) ? sample(n_fft - n) : 0.f;
+        e[i] = a + bb;
+        o[i] = (n < H) ? a - bb : 0.f;
+        nyq += (n & 1) ? -e[i] : e[i];
+      }
+      float hi[8], mid[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float h = __bfloat162float(__float2bfloat16_rn(e[i]));
+        const float r1 = e[i] - h;
+        const float md = __bfloat162float(__float2bfloat16_rn(r1));
+        hi[i] = h; mid[i] = md; lo[i] = r1 - md;
+      }
+      Vec16<bf16>::store(erow + k0, hi);
+      Vec16<bf16>::store(erow + k0 + split_stride, mid);
+      Vec16<bf16>::store(erow + k0 + 2 * split_stride, lo);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float h = __bfloat162float(__float2bfloat16_rn(o[i]));
+        const float r1 = o[i] - h;
+        const float md = __bfloat162float(__float2bfloat16_rn(r1));
+        hi[i] = h; mid[i] = md; lo[i] = r1 - md;
+      }
+      Vec16<bf16>::store(orow + k0, hi);
+      Vec16<bf16>::store(orow + k0 + split_stride, mid);
+      Vec16<bf16>::store(orow + k0 + 2 * split_stride, lo);
+    }
+    nyq = warp_sum(nyq);
+    if (lane == 0) {
+      const float v0 = sample(0);
+      y0[r] = v0;
+      // Nyquist bin (real): n = 0 term of the alternating sum added; padding columns of the row cleared
+      for (int cidx = H; cidx < ldp; ++cidx) {
+        Re[(size_t)r * ldp + cidx] = cidx == H ? nyq + v0 : 0.f;
+        Im[(size_t)r * ldp + cidx] = 0.f;
       }
     }
-    float hi[8], mid[8], lo[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float v = x[e] * wv[e];
-      const float h = __bfloat162float(__float2bfloat16_rn(v));
-      const float r1 = v - h;
-      const float md = __bfloat162float(__float2bfloat16_rn(r1));
-      hi[e] = h;
-      mid[e] = md;
-      lo[e] = r1 - md;
-    }
-    bf16* dst = A3 + (size_t)r * n_fft + n0;
-    Vec16<bf16>::store(dst, hi);
-    Vec16<bf16>::store(dst + split_stride, mid);
-    Vec16<bf16>::store(dst + 2 * split_stride, lo);
   }
 }
 
-// ------------------------------------------------------------------ banded mel + clamp + log (a3)
-// out[m, j] = log(max(sum_i P[m, start[j] + i] * w[j][i], 1e-6)); the HTK filterbank is 0.5 % dense
-// (<= 14 taps per filter), so the projection is a banded gather, not a GEMM.  One thread per mel bin; each
-// power-spectrum row (4 KB, L2-resident) is staged in shared memory with coalesced 16-byte loads (double
-// buffered), taps are then read from shared memory; output rows are written fully coalesced.
-__global__ void __launch_bounds__(512) mel_band_log_kernel(const float* __restrict__ P, int ldp,
-                                                           const int* __restrict__ start, const int* __restrict__ len,
-                                                           const float* __restrict__ w, int max_band,
-                                                           float* __restrict__ out, size_t rows, int n_mels) {
-  extern __shared__ __align__(16) float prow[];  // [2][ldp]
+// fp32 path companion of the folded DFT GEMMs: y[0] per frame and the (real) Nyquist bin sum_n (-1)^n y[n].  One thread per
+// frame would be uncoalesced; one warp per frame as in fold_split_kernel.
+__global__ void __launch_bounds__(256) dft_edge_kernel(const float* __restrict__ wave, const float* __restrict__ window,
+                                                       float* __restrict__ y0, float* __restrict__ Re,
+                                                       float* __restrict__ Im, int ldp, int S, int T, int hop, int n_fft,
+                                                       int m_off, int rows) {
+  const int H = n_fft / 2, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int m = m_off + r;
+    const int b = m / T, t = m - b * T;
+    const float* w = wave + (size_t)b * S;
+    const int base = t * hop - H;
+    float acc = 0.f, first = 0.f;
+    for (int n = lane; n < n_fft; n += 32) {
+      int j = base + n;
+      j = j < 0 ? -j : j;
+      j = j >= S ? 2 * (S - 1) - j : j;
+      const float v = __ldg(w + j) * __ldg(window + n);
+      if (n == 0) first = v;
+      acc += (n & 1) ? -v : v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      y0[r] = first;
+      for (int cidx = H; cidx < ldp; ++cidx) {
+        Re[(size_t)r * ldp + cidx] = cidx == H ? acc : 0.f;
+        Im[(size_t)r * ldp + cidx] = 0.f;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ power + banded mel + clamp + log (a3)
+// out[m, j] = log(max(sum_i |X[m, start[j] + i]|^2 * w[j][i], 1e-6)) with |X|^2 = re^2 + im^2 from the two folded-DFT
+// products.  The HTK filterbank is 0.5 % dense (<= 14 taps per filter), so the projection is a banded gather, not a
+// GEMM.  One thread per mel bin with its taps in registers; MEL_ROWS spectrum rows (L2-resident) are staged per
+// iteration with coalesced 16-byte loads (re and im combined to power on the way into shared memory), so every
+// barrier covers MEL_ROWS rows of loads in flight; output rows are written fully coalesced.
+constexpr int MEL_ROWS = 4;
+__global__ void __launch_bounds__(512) mel_band_log_kernel(const float* __restrict__ Re, const float* __restrict__ Im,
+                                                           int ldp, const int* __restrict__ start,
+                                                           const int* __restrict__ len, const float* __restrict__ w,
+                                                           int max_band, float* __restrict__ out, size_t rows,
+                                                           int n_mels) {
+  extern __shared__ __align__(16) float prow[];  // [MEL_ROWS][ldp]
   const int tid = threadIdx.x;
   const int j = tid;
   int s0 = 0, n = 0;
@@ -544,19 +606,36 @@ __global__ void __launch_bounds__(512) mel_band_log_kernel(const float* __restri
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) wv[i] = (j < n_mels && i < n) ? w[(size_t)j * max_band + i] : 0.f;
+  const bool wide = __syncthreads_or(n > 16) != 0;
   const int nvec = ldp >> 2;
-  int buf = 0;
-  for (size_t m = blockIdx.x; m < rows; m += gridDim.x, buf ^= 1) {
-    float* pr = prow + (size_t)buf * ldp;
-    const float4* src = reinterpret_cast<const float4*>(P + m * ldp);
-    for (int i = tid; i < nvec; i += blockDim.x) reinterpret_cast<float4*>(pr)[i] = src[i];
-    __syncthreads();  // row staged; the other buffer is free again once everyone passed this barrier
+  for (size_t m0 = (size_t)blockIdx.x * MEL_ROWS; m0 < rows; m0 += (size_t)gridDim.x * MEL_ROWS) {
+    const int nr = (int)min((size_t)MEL_ROWS, rows - m0);
+    __syncthreads();  // previous rows fully consumed
+    for (int i = tid; i < nr * nvec; i += blockDim.x) {
+      const int r = i / nvec, c = i - r * nvec;
+      const float4 a = reinterpret_cast<const float4*>(Re + (m0 + r) * ldp)[c];
+      const float4 b = reinterpret_cast<const float4*>(Im + (m0 + r) * ldp)[c];
+      reinterpret_cast<float4*>(prow + (size_t)r * ldp)[c] =
+          make_float4(a.x * a.x + b.x * b.x, a.y * a.y + b.y * b.y, a.z * a.z + b.z * b.z, a.w * a.w + b.w * b.w);
+    }
+    __syncthreads();
     if (j < n_mels) {
-      float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < n) acc = fmaf(pr[s0 + i], wv[i], acc);
-      out[m * n_mels + j] = logf(fmaxf(acc, 1e-6f));
+      for (int r = 0; r < MEL_ROWS; ++r) {
+        if (r < nr) {
+          const float* pr = prow + (size_t)r * ldp;
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < n) acc = fmaf(pr[s0 + i], wv[i], acc);
+          if (wide) {  // block-uniform: only filterbanks with bands of more than 16 taps pay for the second half
+#pragma unroll
+            for (int i = 16; i < 32; ++i)
+              if (i < n) acc = fmaf(pr[s0 + i], wv[i], acc);
+          }
+          out[(m0 + r) * n_mels + j] = logf(fmaxf(acc, 1e-6f));
+        }
+      }
     }
   }
 }

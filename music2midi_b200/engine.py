@@ -47,7 +47,7 @@ class Engine:
     reference's web UI shares one model between Flask threads, webui.py:61,90-93)."""
 
     def __init__(self, device: torch.device, precision: str = "fp32", max_enc_len: int = 512,
-                 overrides: Optional[Mapping[str, int]] = None):
+                 overrides: Optional[Mapping[str, int]] = None, max_distance: int = 128):
         self.lib = _lib.load()
         device = torch.device(device)
         if device.type != "cuda":
@@ -68,6 +68,7 @@ class Engine:
         check(self.lib.m2m_ctx_create(C.byref(cfg), self.device.index, C.byref(self._ctx)))
         self._lock = threading.RLock()
         self.model_ready = False
+        self.max_distance = int(max_distance)  # T5Config.relative_attention_max_distance (bucket LUTs are built with it)
 
     # ------------------------------------------------------------------ lifetime / weights
     def close(self):
@@ -93,9 +94,9 @@ class Engine:
             g = self.cfg
             n_enc = 2 * g.max_enc_len - 1
             rel = torch.arange(n_enc, dtype=torch.long) - (g.max_enc_len - 1)
-            enc = relative_position_bucket(rel, True, g.n_buckets).to(torch.int32).contiguous().numpy()
-            dec = relative_position_bucket(-torch.arange(g.max_positions, dtype=torch.long), False,
-                                           g.n_buckets).to(torch.int32).contiguous().numpy()
+            enc = relative_position_bucket(rel, True, g.n_buckets, self.max_distance).to(torch.int32).contiguous().numpy()
+            dec = relative_position_bucket(-torch.arange(g.max_positions, dtype=torch.long), False, g.n_buckets,
+                                           self.max_distance).to(torch.int32).contiguous().numpy()
             check(self.lib.m2m_set_bucket_luts(self._ctx, enc.ctypes.data_as(C.c_void_p), enc.size,
                                                dec.ctypes.data_as(C.c_void_p), dec.size))
             check(self.lib.m2m_finalize_weights(self._ctx))

@@ -166,16 +166,29 @@ class Music2MIDI(nn.Module):
             lo_clip, hi_clip = dist_mod.shard_range(len(padded), torch.distributed.get_rank(),
                                                     torch.distributed.get_world_size())
         local = padded[lo_clip:hi_clip]
+        n_local = sum(counts[lo_clip:hi_clip])
         if local:
-            wave = torch.from_numpy(np.concatenate(local)).to(self.device)
-            rows = self.generate_tokens(wave, split, cond_index, max_length=1024)
-            tok = torch.zeros(len(rows), 1024, dtype=torch.int16, device=self.device)
-            for i, r in enumerate(rows):
-                tok[i, : r.numel()] = r.to(torch.int16)
+            # one pinned staging buffer for all local segments, then the host-buffer entry point of the library: the
+            # upload of device batch i + 1 overlaps the decode of batch i, tokens come back as int16 (m2m_transcribe_host)
+            stage = torch.empty(n_local, split, dtype=torch.float32, pin_memory=True)
+            flat, pos = stage.view(-1).numpy(), 0
+            for y in local:
+                flat[pos:pos + len(y)] = y
+                pos += len(y)
+            n_embeds = len(self.model.conditioning.embeds)
+            cond = np.zeros((n_local, n_embeds), dtype=np.int64)
+            if cond_index is not None:
+                cond += np.asarray(torch.Tensor(cond_index).long().numpy(), dtype=np.int64)
+            inf = self.config.get("inference", {}) or {}
+            chunk = int(inf.get("device_batch_size", inf.get("batch_size", 128)))
+            toks, _ = self.model.engine().transcribe_host(stage.numpy(), cond, 1024, device_batch=chunk)
+            tok = torch.from_numpy(toks)
         else:
-            tok = torch.zeros(0, 1024, dtype=torch.int16, device=self.device)
+            tok = torch.zeros(0, 1024, dtype=torch.int64)
         if distributed and torch.distributed.is_initialized():
-            tok = dist_mod.gather_tokens(tok, sum(counts))
+            world = torch.distributed.get_world_size()
+            rows = [sum(counts[slice(*dist_mod.shard_range(len(padded), r, world))]) for r in range(world)]
+            tok = dist_mod.gather_tokens(tok.to(self.device), sum(counts), counts=rows)
         tok = tok.to(torch.int64).cpu()
         out, pos = [], 0
         for n in counts:

@@ -13,6 +13,7 @@ parameter container with HF's module/parameter names and all arithmetic runs in 
 from __future__ import annotations
 
 import os
+import threading
 import weakref
 from types import SimpleNamespace
 from typing import Optional
@@ -171,6 +172,7 @@ class T5Transformer(nn.Module):
         self.precision = precision or os.environ.get("M2M_PRECISION") or inf.get("precision", "fp32")
         self._engine: Optional[Engine] = None
         self._engine_key = None
+        self._engine_lock = threading.Lock()  # the reference's web UI shares one model between Flask threads
         ref = weakref.ref(self)
         # the sub-modules share this model's context instead of building their own
         object.__setattr__(self.spectrogram, "_owner_engine", lambda: ref().engine())
@@ -197,19 +199,24 @@ class T5Transformer(nn.Module):
                 "There is no CPU fallback."
             )
         key = (str(dev),) + self._weights_key()
-        if self._engine is None or self._engine_key != key:
-            if self._engine is not None:
-                self._engine.close()
-            t5 = self.t5config
-            eng = Engine(dev, self.precision, overrides=dict(
-                n_layers=t5.num_layers, d_model=t5.d_model, d_kv=t5.d_kv, n_heads=t5.num_heads, d_ff=t5.d_ff,
-                vocab=t5.vocab_size, n_buckets=t5.relative_attention_num_buckets, max_positions=t5.n_positions,
-                n_fft=self.spectrogram.n_fft, hop=self.spectrogram.hop_length, n_cond=len(self.conditioning.embeds),
-                pad_id=t5.pad_token_id, bos_id=t5.decoder_start_token_id, eos_id=t5.eos_token_id,
-                ln_eps=t5.layer_norm_epsilon))
-            eng.load_state_dict(self.state_dict())
-            self._engine, self._engine_key = eng, key
-        return self._engine
+        with self._engine_lock:  # one creator / swapper at a time; an old context is closed only under its own lock
+            if self._engine is None or self._engine_key != key:
+                if self._engine is not None:
+                    old = self._engine
+                    with old._lock:  # no other thread is inside a library call on the old context
+                        old.close()
+                t5 = self.t5config
+                inf = self.config.get("inference", {}) or {}
+                eng = Engine(dev, self.precision, max_enc_len=int(inf.get("max_enc_len", 512)),
+                             max_distance=t5.relative_attention_max_distance, overrides=dict(
+                    n_layers=t5.num_layers, d_model=t5.d_model, d_kv=t5.d_kv, n_heads=t5.num_heads, d_ff=t5.d_ff,
+                    vocab=t5.vocab_size, n_buckets=t5.relative_attention_num_buckets, max_positions=t5.n_positions,
+                    n_fft=self.spectrogram.n_fft, hop=self.spectrogram.hop_length, n_cond=len(self.conditioning.embeds),
+                    pad_id=t5.pad_token_id, bos_id=t5.decoder_start_token_id, eos_id=t5.eos_token_id,
+                    ln_eps=t5.layer_norm_epsilon))
+                eng.load_state_dict(self.state_dict())
+                self._engine, self._engine_key = eng, key
+            return self._engine
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
