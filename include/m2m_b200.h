@@ -191,11 +191,13 @@ int m2m_stats_get(m2m_ctx* ctx, m2m_stats* out);
  * (default: tcgen05 in M2M_BF16 contexts, fp32 CUDA-core in M2M_FP32 contexts),
  * bit6 = use the CUDA-core sequence attention instead of the fused tcgen05 encoder attention,
  * bit7 = bf16 contexts: run the decode step as separate RMSNorm / GEMM launches instead of the cluster-phased
- * tcgen05 GEMM chain (A/B testing). */
+ * tcgen05 GEMM chain (A/B testing), bit8 = prefill GEMMs on the one-tile-per-CTA tcgen05 kernel instead of the
+ * persistent one (A/B testing). */
 int m2m_set_flags(m2m_ctx* ctx, uint32_t flags);
 
 /* Test hook (tests/test_gpu_gemm.py): d_C fp32 [M,N] = A[M,K] . W[N,K]^T with bf16 device operands, through
- * path 0 = CUDA-core kernel, 1 = tcgen05 kernel (automatic tile), 2 / 3 = tcgen05 with BN = 64 / 128.
+ * path 0 = CUDA-core kernel, 1 = tcgen05 kernel (automatic tile), 2 / 3 = tcgen05 with BN = 64 / 128,
+ * 4 / 5 = persistent tcgen05 kernel (double-buffered TMEM accumulators) with the automatic tile / BN = 192.
  * Synchronises the stream, so a faulting kernel is reported by this call. */
 int m2m_debug_gemm_bf16(m2m_ctx* ctx, const void* d_A, const void* d_W, int M, int N, int K, float* d_C, int path,
                         void* stream);

@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
 #include "chain_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "kernels.cuh"
 
 namespace m2m {
@@ -229,7 +230,10 @@ static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K
   cudaError_t e;
   if constexpr (std::is_same<T, bf16>::value) {
     if (!(c->flags & 8u) && tc::supported(M, N, K, lda)) {
-      e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms);
+      if (st == nullptr && !(c->flags & 256u) && tc::persistent_worthwhile(M, N, c->num_sms))
+        e = tc::launch2(A, lda, W, M, N, K, epi, s, c->num_sms);  // prefill-sized: persistent, double-buffered TMEM
+      else
+        e = tc::launch(A, lda, W, M, N, K, epi, st, s, c->num_sms);
       if (e != cudaSuccess) {
         set_error("tcgen05 gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
         return M2M_ERR_CUDA;
@@ -1553,6 +1557,12 @@ int m2m_debug_gemm_bf16(m2m_ctx* c, const void* d_A, const void* d_W, int M, int
   } else if (path == 3) {
     M2M_REQUIRE(tc::supported(M, N, K, K), "debug gemm: shape not supported by the tcgen05 kernel");
     e = tc::launch_cfg<128, 3>(A, K, W, M, N, K, EpiStore<float>{d_C, N}, nullptr, s);
+  } else if (path == 4) {
+    M2M_REQUIRE(tc::supported(M, N, K, K), "debug gemm: shape not supported by the tcgen05 kernel");
+    e = tc::launch2(A, K, W, M, N, K, EpiStore<float>{d_C, N}, s, c->num_sms);
+  } else if (path == 5) {
+    M2M_REQUIRE(tc::supported(M, N, K, K), "debug gemm: shape not supported by the tcgen05 kernel");
+    e = tc::launch2_cfg<192>(A, K, W, M, N, K, EpiStore<float>{d_C, N}, s, c->num_sms);
   } else {
     e = launch_gemm_simt(RowMajorA<bf16>{A, K}, W, K, M, N, K, EpiStore<float>{d_C, N}, nullptr, s, c->num_sms);
   }

@@ -13,8 +13,10 @@
 //                 .multicast::cluster): the ring has six stages and CTA r owns stage r of everybody's ring - it issues
 //                 tiles r, r + 6, ... after all six MMA issuers released the stage (tcgen05.commit multicast onto its
 //                 a_empty barrier).  Waits for the phase handshake: A of phase p is the output of phase p-1 of ALL CTAs
-//   warp 1      : B producer  - TMA loads of the weight sub-tiles (5-deep ring of 16 KB slots); weights depend on
-//                 nothing, so this warp free-runs ahead across phase boundaries (prefetch under the handshake)
+//   warp 1      : B producer  - TMA loads of the weight sub-tiles into a 112 KB circular buffer; the tiles one MMA round
+//                 consumes (all sub-tiles of a k-block, or of two k-blocks when they are small) form a GROUP with ONE
+//                 mbarrier, because a barrier wait costs the MMA issuer ~250 cycles whatever it waits for.  Weights
+//                 depend on nothing, so this warp free-runs ahead across phase boundaries (prefetch under the handshake)
 //   warp 2      : MMA issuer  - one lane, tcgen05.mma cta_group::1 kind::f16, M = 128, N = sub-tile rows, fp32
 //                 accumulators in TMEM (<= 384 columns per phase)
 //   warps 3-10  : epilogue    - two warps per TMEM lane quarter, each half of the columns: tcgen05.ld (thread = row),
@@ -40,7 +42,9 @@ namespace tc {
 constexpr int CHAIN_CS = 6;
 constexpr int CHAIN_MAX_PHASES = 4;
 constexpr int CHAIN_A_STAGES = CHAIN_CS;  // stage r of every CTA's ring is filled by CTA r (multicast)
-constexpr int CHAIN_B_STAGES = 7;
+constexpr int CHAIN_A_PAIRS = CHAIN_A_STAGES / 2;  // A tiles are consumed two at a time (one barrier per pair of stages)
+constexpr int CHAIN_B_KB = 112;      // weight ring: a circular byte buffer of 112 KB, allocated in 1 KB units
+constexpr int CHAIN_B_GROUPS = 8;    // weight groups in flight (one mbarrier pair each)
 constexpr int CHAIN_EPI_WARPS = 8;   // two warps per TMEM lane quarter (each takes half of the phase's columns)
 constexpr int CHAIN_SS = 2 * CHAIN_CS;  // partial sums of squares per row: one per (column slice, epilogue half)
 constexpr int CHAIN_STAGE_BYTES = 32 * 36 * 4;  // per epilogue warp: 32 x 32 fp32 transposition tile, padded rows
@@ -51,7 +55,7 @@ constexpr int CHAIN_THREADS = 32 * (3 + CHAIN_EPI_WARPS);
 // The epilogue's transposition tiles ALIAS the A ring: between the last MMA of a phase and the handshake that ends it no
 // A tile is live, and no peer multicasts into this CTA's ring before this CTA's own epilogue has arrived on the handshake.
 static_assert(CHAIN_EPI_WARPS * CHAIN_STAGE_BYTES <= CHAIN_A_STAGES * CHAIN_A_BYTES, "staging must fit in the A ring");
-constexpr int CHAIN_SMEM = 1024 + CHAIN_A_STAGES * CHAIN_A_BYTES + CHAIN_B_STAGES * CHAIN_B_BYTES;
+constexpr int CHAIN_SMEM = 1024 + CHAIN_A_STAGES * CHAIN_A_BYTES + CHAIN_B_KB * 1024;
 
 enum ChainEpi : int {
   CH_RESIDUAL = 0,  // x[m, n] += acc; xb[m, n] = bf16(x); ss[m][slice] = sum_n x^2          (N per CTA = 64)
@@ -241,17 +245,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// gelu_new with the hardware tanh (abs. error ~5e-4 on tanh, below the bf16 rounding of the result)
-__device__ __forceinline__ float gelu_new_fast(float x) {
-  const float k = 0.7978845608028654f;
-  return 0.5f * x * (1.0f + tanh_fast(k * (x + 0.044715f * (x * x * x))));
-}
-
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -264,8 +257,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
   uint8_t* sA = smem;
   uint8_t* sB = smem + CHAIN_A_STAGES * CHAIN_A_BYTES;
   uint8_t* sStage = sA;  // aliases the A ring (see CHAIN_SMEM)
-  __shared__ __align__(8) uint64_t a_full[CHAIN_A_STAGES], a_empty[CHAIN_A_STAGES];
-  __shared__ __align__(8) uint64_t b_full[CHAIN_B_STAGES], b_empty[CHAIN_B_STAGES];
+  __shared__ __align__(8) uint64_t a_full[CHAIN_A_PAIRS], a_empty[CHAIN_A_PAIRS];
+  __shared__ __align__(8) uint64_t b_full[CHAIN_B_GROUPS], b_empty[CHAIN_B_GROUPS];
   __shared__ __align__(8) uint64_t acc_full, acc_empty, sync_bar;
   __shared__ uint32_t tmem_base_smem;
 
@@ -277,15 +270,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
     CH_TRACE(0);
     int total_a = 0;
     for (int p = 0; p < P.n_phases; ++p) total_a += P.ph[p].kblocks;
-    for (int s = 0; s < CHAIN_A_STAGES; ++s) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], CHAIN_CS);  // used in CTA s only: one tcgen05.commit per CTA of the cluster
+    for (int j = 0; j < CHAIN_A_PAIRS; ++j) {
+      mbar_init(&a_full[j], 1);
+      mbar_init(&a_empty[j], CHAIN_CS);  // used in CTAs 2j and 2j+1 (the owners of the pair's two stages): one commit per CTA
     }
-    // arm the first use of every stage (later uses are armed by the MMA issuer once it has drained the stage)
-    for (int s = 0; s < CHAIN_A_STAGES && s < total_a; ++s) mbar_expect_tx(&a_full[s], CHAIN_A_BYTES);
-    for (int s = 0; s < CHAIN_B_STAGES; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+    // arm the first use of every stage pair (later uses are armed by the MMA issuer once it has drained the pair)
+    for (int j = 0; j < CHAIN_A_PAIRS && 2 * j < total_a; ++j) mbar_expect_tx(&a_full[j], 2 * CHAIN_A_BYTES);
+    for (int g = 0; g < CHAIN_B_GROUPS; ++g) {
+      mbar_init(&b_full[g], 1);
+      mbar_init(&b_empty[g], 1);
     }
     mbar_init(&acc_full, 1);
     mbar_init(&acc_empty, 1);
@@ -315,8 +308,19 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
   uint32_t total_a = 0;
   for (int p = 0; p < P.n_phases; ++p) total_a += (uint32_t)P.ph[p].kblocks;
 
+  // weight groups: what one MMA round consumes.  Sub-tiles of one k-block, or of a pair of k-blocks when a k-block's
+  // weights are <= 16 KB.  Both the producer and the MMA issuer walk the same deterministic allocation sequence.
+  auto group_kblocks = [](int n_sub, int sub_rows) { return n_sub * sub_rows * (BK * 2) <= 16384 ? 2 : 1; };
+  auto ring_alloc = [](uint32_t& head, uint32_t kb_units) {
+    if (head + kb_units > (uint32_t)CHAIN_B_KB) head = 0;  // a group is contiguous: skip the tail of the buffer
+    const uint32_t off = head;
+    head += kb_units;
+    return off;
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer (stage `crank` of all six rings)
+    const uint32_t pj = (uint32_t)crank >> 1;  // this stage's pair
     uint32_t ai = 0;
     for (int p = 0; p < P.n_phases; ++p) {
       const int kblocks = P.ph[p].kblocks;
@@ -331,9 +335,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
           if (lane == 0) CH_TRACE(8 + 8 * p + 0);
         }
         const uint32_t u = ai / CHAIN_A_STAGES;
-        if (u > 0) mbar_wait_cluster_u(a_empty_u + 8u * crank, (u - 1) & 1u);  // all six MMA issuers released the stage
+        if (u > 0) mbar_wait_cluster_u(a_empty_u + 8u * pj, (u - 1) & 1u);  // all six MMA issuers released the pair
         if (elect_one())
-          tma_load_2d_multicast_u(sA_u + crank * CHAIN_A_BYTES, tm, a_full_u + 8u * crank, kb * BK, m0,
+          tma_load_2d_multicast_u(sA_u + crank * CHAIN_A_BYTES, tm, a_full_u + 8u * pj, kb * BK, m0,
                                   (uint16_t)((1u << CHAIN_CS) - 1));
         __syncwarp();
       }
@@ -341,72 +345,104 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ B producer (free-running weight prefetch)
-    uint32_t sb = 0, par = 1;  // first pass over the ring: the "previous" phase of an initialised barrier is complete
+    uint32_t head = 0, g = 0, tail = 0;          // ring head (KB), next group, oldest group still in flight
+    uint32_t in_off[CHAIN_B_GROUPS], in_sz[CHAIN_B_GROUPS];  // extents of the groups in flight (indexed g % 8)
+#pragma unroll
+    for (int i = 0; i < CHAIN_B_GROUPS; ++i) in_off[i] = in_sz[i] = 0;
     for (int p = 0; p < P.n_phases; ++p) {
       const int kblocks = P.ph[p].kblocks, n_sub = P.ph[p].n_sub, sub_rows = P.ph[p].sub_rows;
       const CUtensorMap* tm = &P.ph[p].tmB;
       const int b_row0 = crank * n_sub * sub_rows;  // rows beyond the matrix are zero-filled by TMA
-      const uint32_t bytes = (uint32_t)sub_rows * (BK * 2);
-      for (int kb = 0; kb < kblocks; ++kb)
-        for (int sub = 0; sub < n_sub; ++sub) {
-          mbar_wait_u(b_empty_u + 8u * sb, par);
-          if (elect_one()) {
-            mbar_expect_tx_u(b_full_u + 8u * sb, bytes);
-            tma_load_2d_u(sB_u + sb * CHAIN_B_BYTES, tm, b_full_u + 8u * sb, kb * BK, b_row0 + sub * sub_rows);
+      const int gk = group_kblocks(n_sub, sub_rows);
+      const uint32_t tile_bytes = (uint32_t)sub_rows * (BK * 2);
+      const uint32_t gsz = (uint32_t)(gk * n_sub) * tile_bytes >> 10;
+      for (int kb = 0; kb < kblocks; kb += gk, ++g) {
+        const uint32_t off = ring_alloc(head, gsz);
+        // wait until no group in flight overlaps [off, off + gsz) and a barrier pair is free
+        for (;;) {
+          bool busy = g - tail >= (uint32_t)CHAIN_B_GROUPS;
+#pragma unroll
+          for (int i = 0; i < CHAIN_B_GROUPS; ++i) {
+            const uint32_t gi = tail + (((uint32_t)i - tail) & (CHAIN_B_GROUPS - 1));  // the group index with gi % 8 == i, gi >= tail
+            if (gi < g && in_off[i] < off + gsz && off < in_off[i] + in_sz[i]) busy = true;
           }
-          __syncwarp();
-          if (++sb == CHAIN_B_STAGES) {
-            sb = 0;
-            par ^= 1u;
-          }
+          if (!busy) break;
+          mbar_wait_u(b_empty_u + 8u * (tail & (CHAIN_B_GROUPS - 1)), (tail / CHAIN_B_GROUPS) & 1u);
+          ++tail;
         }
+        const uint32_t slot = g & (CHAIN_B_GROUPS - 1);
+#pragma unroll
+        for (int i = 0; i < CHAIN_B_GROUPS; ++i)
+          if (i == (int)slot) {
+            in_off[i] = off;
+            in_sz[i] = gsz;
+          }
+        if (elect_one()) {
+          mbar_expect_tx_u(b_full_u + 8u * slot, gsz << 10);
+          uint32_t dst = sB_u + (off << 10);
+          for (int kk = 0; kk < gk; ++kk)
+            for (int sub = 0; sub < n_sub; ++sub, dst += tile_bytes)
+              tma_load_2d_u(dst, tm, b_full_u + 8u * slot, (kb + kk) * BK, b_row0 + sub * sub_rows);
+        }
+        __syncwarp();
+      }
       if (lane == 0) CH_TRACE(8 + 8 * p + 7);
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
-    // Measured (tools/chain_trace.py): a round (two barrier waits, fence, four UMMAs, two commits, one expect_tx) costs
-    // this warp ~900 cycles however deep the rings are and however few UMMAs it issues: the chain is bound by the
-    // issue latency of the barrier / tensor-core control instructions, not by data or tensor throughput.
+    // Measured (tools/chain_trace.py): a barrier wait costs this warp ~250 cycles and a commit ~80 even when nothing
+    // is outstanding, while four UMMAs cost ~60: the chain is bound by the issue latency of the barrier / tensor-core
+    // control instructions, not by data or tensor throughput.  Hence one wait per PAIR of A tiles and one per weight
+    // GROUP: 44 waits per four-phase launch instead of 94.
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    uint32_t ai = 0, sa = 0, pa = 0, sb = 0, pb = 0;
+    const uint32_t total_pairs = total_a >> 1;
+    uint32_t pi = 0, sp = 0, pa = 0, head = 0, g = 0;
     for (int p = 0; p < P.n_phases; ++p) {
       const int kblocks = P.ph[p].kblocks, n_sub = P.ph[p].n_sub, sub_rows = P.ph[p].sub_rows;
+      const int gk = group_kblocks(n_sub, sub_rows);
+      const uint32_t tile_bytes = (uint32_t)sub_rows * (BK * 2);
+      const uint32_t gsz = (uint32_t)(gk * n_sub) * tile_bytes >> 10;
       if (p > 0) mbar_wait_u(acc_empty_u, (uint32_t)(p - 1) & 1u);  // epilogue of the previous phase has drained TMEM
       const uint32_t idesc = make_idesc(sub_rows);
-      for (int kb = 0; kb < kblocks; ++kb, ++ai) {
-        mbar_wait_u(a_full_u + 8u * sa, pa);
-        const bool detail = P.trace != nullptr && p == P.trace_phase && kb < 32 && lane == 0;
+      for (int kb = 0; kb < kblocks; kb += 2, ++pi) {
+        mbar_wait_u(a_full_u + 8u * sp, pa);
+        const bool detail = P.trace != nullptr && p == P.trace_phase && kb < 64 && lane == 0;
         if (kb == 0 && lane == 0) CH_TRACE(8 + 8 * p + 2);
-        if (detail) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 0);
-        const uint64_t adesc = make_smem_desc(sA_u + sa * CHAIN_A_BYTES);
-        for (int sub = 0; sub < n_sub; ++sub) {
-          mbar_wait_u(b_full_u + 8u * sb, pb);
-          if (detail && sub == n_sub - 1) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (detail) CH_TRACE(CHAIN_TRACE_DETAIL + 2 * kb + 0);
+        uint32_t boff = 0;
+        for (int kk = 0; kk < 2; ++kk) {
+          if (kk == 0 || gk == 1) {  // next weight group
+            boff = sB_u + (ring_alloc(head, gsz) << 10);
+            mbar_wait_u(b_full_u + 8u * (g & (CHAIN_B_GROUPS - 1)), (g / CHAIN_B_GROUPS) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          if (detail && kk == 1) CH_TRACE(CHAIN_TRACE_DETAIL + 2 * kb + 1);
           if (elect_one()) {
-            const uint64_t bdesc = make_smem_desc(sB_u + sb * CHAIN_B_BYTES);
-            const uint32_t tacc = tm_u + (uint32_t)(sub * sub_rows);
+            const uint64_t adesc = make_smem_desc(sA_u + (2 * sp + kk) * CHAIN_A_BYTES);
+            for (int sub = 0; sub < n_sub; ++sub, boff += tile_bytes) {
+              const uint64_t bdesc = make_smem_desc(boff);
+              const uint32_t tacc = tm_u + (uint32_t)(sub * sub_rows);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_u(b_empty_u + 8u * sb);
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | kk | k) != 0 ? 1u : 0u);
+            }
+            if (kk == 1 || gk == 1) umma_commit_u(b_empty_u + 8u * (g & (CHAIN_B_GROUPS - 1)));
+          } else {
+            boff += (uint32_t)n_sub * tile_bytes;
           }
           __syncwarp();
-          if (detail && sub == n_sub - 1) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 2);
-          if (++sb == CHAIN_B_STAGES) {
-            sb = 0;
-            pb ^= 1u;
-          }
+          if (kk == 1 || gk == 1) ++g;
         }
+        if (detail) CH_TRACE(CHAIN_TRACE_DETAIL + 2 * kb + 2);
         if (elect_one()) {
-          // release the stage to its owner (CTA sa), then arm this CTA's barrier for the stage's next tile
-          umma_commit_multicast_u(a_empty_u + 8u * sa, (uint16_t)(1u << sa));
-          if (ai + CHAIN_A_STAGES < total_a) mbar_expect_tx_u(a_full_u + 8u * sa, CHAIN_A_BYTES);
+          // release the two stages to their owners (CTAs 2 sp, 2 sp + 1), then arm this CTA's barrier for the pair's next tiles
+          umma_commit_multicast_u(a_empty_u + 8u * sp, (uint16_t)(3u << (2 * sp)));
+          if (pi + CHAIN_A_PAIRS < total_pairs) mbar_expect_tx_u(a_full_u + 8u * sp, 2 * CHAIN_A_BYTES);
         }
         __syncwarp();
-        if (detail) CH_TRACE(CHAIN_TRACE_DETAIL + 4 * kb + 3);
-        if (++sa == CHAIN_A_STAGES) {
-          sa = 0;
+        if (detail) CH_TRACE(CHAIN_TRACE_DETAIL + 2 * kb + 3);
+        if (++sp == CHAIN_A_PAIRS) {
+          sp = 0;
           pa ^= 1u;
         }
       }
@@ -472,6 +508,23 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
           } else {
             tmem_ld16(tmem_base + lane_addr + (uint32_t)c0, v);
           }
+          if (ph.epi == CH_GELU) {
+            // gated GELU in the row domain: the 16 (wi_0, wi_1) pairs of this thread's row are independent (full ILP on
+            // the tanh chains), the result is 16 bf16 = 32 B = one full sector per thread: no transposition needed
+            if (m_tmem < P.M) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float g0 = gelu_new_fast(__uint_as_float(v[4 * j]) * rstd) * (__uint_as_float(v[4 * j + 1]) * rstd);
+                const float g1 = gelu_new_fast(__uint_as_float(v[4 * j + 2]) * rstd) * (__uint_as_float(v[4 * j + 3]) * rstd);
+                pk[j] = pack_bf16(g0, g1);
+              }
+              bf16* op = reinterpret_cast<bf16*>(ph.out0) + (size_t)m_tmem * ph.ld + ((n_cta0 + c0) >> 1);
+              *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              if (w == 32) *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (4 * j < w)
@@ -509,15 +562,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
                 sq += __shfl_xor_sync(0xffffffffu, sq, 4);
                 if ((lane & 7) == 0 && ok) sp[(size_t)i * 4 * CHAIN_SS] = sq;
               }
-            } else if (ph.epi == CH_GELU) {  // W rows interleaved: (wi_0[j], wi_1[j]) pairs -> gg[m, n / 2 .. n / 2 + 2)
-              bf16* op = reinterpret_cast<bf16*>(ph.out0) + (size_t)m_t0 * ph.ld + (n >> 1);
-              const size_t step = (size_t)4 * ph.ld;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 a = *reinterpret_cast<const float4*>(&tile[4 * i + trow][tcol]);
-                if (4 * i < rows_left)
-                  *reinterpret_cast<uint32_t*>(op + i * step) = pack_bf16(gelu_new_fast(a.x) * a.y, gelu_new_fast(a.z) * a.w);
-              }
             } else if (ph.epi == CH_LOGITS) {
               if (n < ph.n_total) {
                 float* op = reinterpret_cast<float*>(ph.out0) + (size_t)m_t0 * ph.ld + n;
@@ -527,7 +571,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
                   if (4 * i < rows_left)
                     *reinterpret_cast<float4*>(op + i * step) = *reinterpret_cast<const float4*>(&tile[4 * i + trow][tcol]);
               }
-            } else {  // CH_STORE / CH_QKV: four bf16 per lane
+            } else {  // CH_STORE / CH_QKV: four bf16 per lane (measured faster than 64-byte row-domain stores)
               bf16* op;
               size_t step;
               bool ok = true;
@@ -606,7 +650,8 @@ inline cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream) {
 // fills one phase; `W` has w_rows rows (>= the rows any CTA's box touches or zero-filled beyond)
 inline bool chain_phase(ChainPhase* ph, const bf16* A, int M, int K, const bf16* W, int w_rows, int n_sub, int sub_rows,
                         int n_total, int epi) {
-  if (K % BK != 0 || sub_rows % 16 != 0 || sub_rows > CHAIN_B_ROWS || n_sub * sub_rows > 384) return false;
+  // A tiles are consumed in pairs: K must be a multiple of 128
+  if (K % (2 * BK) != 0 || sub_rows % 16 != 0 || sub_rows > CHAIN_B_ROWS || n_sub * sub_rows > 384) return false;
   if (!make_map(&ph->tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM)) return false;
   if (!make_map(&ph->tmB, W, (uint64_t)w_rows, (uint64_t)K, (uint64_t)K, (uint32_t)sub_rows)) return false;
   ph->kblocks = K / BK;

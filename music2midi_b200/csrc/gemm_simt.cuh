@@ -10,6 +10,8 @@
 // Operands are staged K-major in shared memory, next tile prefetched to registers during the FMAs.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace m2m {
@@ -71,6 +73,14 @@ struct EpiResidual {  // X[m, n] += v   (fp32 residual stream)
     x.x += v[0]; x.y += v[1]; x.z += v[2]; x.w += v[3];
     *p = x;
   }
+  // split form for kernels that fetch the residual early (all loads of a chunk in flight before the first store)
+  __device__ __forceinline__ float4 fetch(int m, int n) const {
+    return *reinterpret_cast<const float4*>(X + (size_t)m * ld + n);
+  }
+  __device__ __forceinline__ void combine(int m, int n, const float v[4], float4 x) const {
+    x.x += v[0]; x.y += v[1]; x.z += v[2]; x.w += v[3];
+    *reinterpret_cast<float4*>(X + (size_t)m * ld + n) = x;
+  }
 };
 // X[m, n] += v and XB[m, n] = bf16(X[m, n]): the bf16 copy feeds the next fused RMSNorm-GEMM
 struct EpiResidualDual {
@@ -93,8 +103,14 @@ struct EpiGatedGelu {
   int ld;
   __device__ __forceinline__ void operator()(int m, int n, const float v[4], const DecState*) const {
     TC* p = G + (size_t)m * ld + (n >> 1);
-    p[0] = from_f<TC>(gelu_new(v[0]) * v[1]);
-    p[1] = from_f<TC>(gelu_new(v[2]) * v[3]);
+    if constexpr (std::is_same<TC, bf16>::value) {
+      // throughput mode: hardware tanh (abs. error ~5e-4, below the bf16 rounding of the result), one 4-byte store
+      __nv_bfloat162 o = __floats2bfloat162_rn(gelu_new_fast(v[0]) * v[1], gelu_new_fast(v[2]) * v[3]);
+      *reinterpret_cast<__nv_bfloat162*>(p) = o;
+    } else {
+      p[0] = from_f<TC>(gelu_new(v[0]) * v[1]);
+      p[1] = from_f<TC>(gelu_new(v[2]) * v[3]);
+    }
   }
 };
 // Decode-step fused QKV: cols [0,I) -> q[m, :], [I,2I) -> K cache, [2I,3I) -> V cache at position t of the

@@ -84,6 +84,13 @@ class Music2MIDI(nn.Module):
         # tied aliases may be absent in checkpoints written by other transformers versions
         tied = {"model.transformer.encoder.embed_tokens.weight", "model.transformer.decoder.embed_tokens.weight"}
         missing = [k for k in missing if k not in tied]
+        if missing == ["model.transformer.lm_head.weight"] and not unexpected:
+            # config.yaml:23 sets tie_word_embeddings: false -> the released checkpoints carry their own lm_head.  One
+            # without it was exported by a transformers version that force-ties the head; running with the randomly
+            # initialised head instead would produce garbage silently.
+            raise RuntimeError("checkpoint has no 'model.transformer.lm_head.weight' (untied lm_head required, "
+                               "tie_word_embeddings: false); re-export it with the head, or copy "
+                               "transformer.shared.weight into that key if the head really is tied")
         if missing or unexpected:
             raise RuntimeError(f"checkpoint mismatch: missing={missing} unexpected={list(unexpected)}")
         return obj

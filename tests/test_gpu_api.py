@@ -143,3 +143,45 @@ def test_generate_many_equals_per_recording_generate(m2m):
         b = [(n.start, n.end, n.pitch, n.velocity) for n in single.instruments[0].notes]
         assert a == b
     assert m2m.generate_many([]) == []
+
+
+def test_checkpoint_to_gpu_inference(state_dict, tmp_path):
+    """webui.py:90 / demo.ipynb:14: Music2MIDI.load_from_checkpoint(ckpt, config_path=...).cuda() -> generate.  A
+    Lightning-style checkpoint ("model." prefix, hyper_parameters) written from the synthetic weights must reproduce
+    the reference's golden tokens through the CUDA path; one without lm_head.weight (an HF >= 5 export, where the
+    head is force-tied) must fail loudly instead of silently running with a random head."""
+    from music2midi.input import ModelInputs
+    from music2midi.model import Music2MIDI
+
+    ck = tmp_path / "m.ckpt"
+    torch.save({"state_dict": {"model." + k: v for k, v in state_dict.items()},
+                "hyper_parameters": {"config_path": DEFAULT_CONFIG_PATH}}, ck)
+    m = Music2MIDI.load_from_checkpoint(str(ck)).cuda()
+    assert m.device.type == "cuda"
+    g = golden("generate.npz")
+    wave = torch.cat([syn.audio_noise(8, 0), syn.audio_tones(8, 0)])
+    cond = torch.stack([torch.arange(16) % 6, torch.arange(16) % 3], 1)
+    toks = m.model.generate(ModelInputs(input_waveform=wave.to(DEV), cond_index=cond.to(DEV)), max_length=160)
+    assert torch.equal(toks.cpu(), torch.from_numpy(g["tokens"].astype(np.int64))[:, :160])
+    # the public entry point on top of it
+    midi = m.generate(audio_y=wave[0].numpy(), cond_index=[0, 0])
+    assert midi.resolution == 384 and len(midi.instruments) == 1
+
+    bad = tmp_path / "no_head.ckpt"
+    torch.save({"state_dict": {"model." + k: v for k, v in state_dict.items() if k != "transformer.lm_head.weight"},
+                "hyper_parameters": {"config_path": DEFAULT_CONFIG_PATH}}, bad)
+    with pytest.raises(RuntimeError, match="lm_head"):
+        Music2MIDI.load_from_checkpoint(str(bad))
+
+
+def test_generate_many_uses_the_host_buffer_path(m2m):
+    """generate_many stages all recordings in one pinned buffer and runs m2m_transcribe_host (double-buffered
+    upload, int16 token read-back): same notes as transcribing the recordings one by one."""
+    g = torch.Generator().manual_seed(11)
+    recs = [(0.1 * torch.randn(n, generator=g)).numpy() for n in (48000, 48000 * 2 + 777, 30000)]
+    many = m2m.generate_many(recs, cond_index=[1, 2])
+    for rec, mm in zip(recs, many):
+        one = m2m.generate(audio_y=rec, cond_index=[1, 2])
+        a = [(n.start, n.end, n.pitch, n.velocity) for n in one.instruments[0].notes]
+        b = [(n.start, n.end, n.pitch, n.velocity) for n in mm.instruments[0].notes]
+        assert a == b

@@ -10,11 +10,11 @@ DEV = "cuda:0"
 SHAPES = [  # (M, N, K): model shapes, ragged M tails, N not a multiple of the tile, long K
     (2560, 1536, 384), (2560, 384, 512), (2560, 2304, 384), (2560, 384, 1152), (2560, 400, 384), (2560, 512, 384),
     (1, 384, 384), (10, 1536, 384), (127, 400, 384), (129, 64, 64), (300, 1024, 384), (190 * 7, 2304, 384),
-    (1000, 2052, 2048), (4096, 256, 128),
+    (1000, 2052, 2048), (4096, 256, 128), (486400 // 8, 1536, 384), (32768, 384, 1152), (20000, 1024, 384),
 ]
 
 
-@pytest.mark.parametrize("path", [0, 1, 2, 3])
+@pytest.mark.parametrize("path", [0, 1, 2, 3, 4, 5])  # 4 / 5: persistent kernel (BN = 256 or 192 / BN = 192)
 def test_gemm_paths_match_fp32_reference(engine_bf16, report, path):
     g = torch.Generator().manual_seed(path)
     worst = 0.0
