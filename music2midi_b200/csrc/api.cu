@@ -483,7 +483,7 @@ static int cross_kv_impl(m2m_ctx* c, const T* enc_out, int B, int L, cudaStream_
 // bf16 contexts run the GEMM chain between the attention kernels as cluster-phased tcgen05 launches
 // (chain_tc.cuh): per step  K0 = QKV(layer 0);  per layer  self-attention, KB = [o-proj + residual | cross-q],
 // cross-attention, KA = [co-proj + residual | Wi + gated GELU | Wffo + residual | QKV(layer + 1) or lm_head].
-// 27 launches per step instead of 72.
+// 26 launches per step instead of 72.
 static bool use_chain(const m2m_ctx* c) {
   const m2m_config& g = c->cfg;
   return g.precision == M2M_BF16 && !(c->flags & 8u) && !(c->flags & 128u) && g.d_model == 64 * tc::CHAIN_CS &&
@@ -673,10 +673,9 @@ static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const in
     M2M_TRY(gemm<T>(c, h, D, (const T*)c->lm_head, B, V, D, EpiStore<float>{logits, V}, st, s));
   }
   TimedScope ts(c, KC_DEC_SELECT, s, step);
-  select_token_kernel<<<B, 128, 0, s>>>(logits, V, tokens, max_length, forced, fin, c->shared, x, D, logits_all, st,
-                                        g.pad_id, g.eos_id, xb, ss, ss ? tc::CHAIN_SS : 0);
-  LAUNCH_CHECK(c);
-  step_advance_kernel<<<1, 1, 0, s>>>(st, forced == nullptr ? 1 : 0);
+  select_token_kernel<<<(B + SELECT_ROWS - 1) / SELECT_ROWS, 32 * SELECT_ROWS, 0, s>>>(
+      logits, V, tokens, max_length, forced, fin, c->shared, x, D, logits_all, st, g.pad_id, g.eos_id, xb, ss,
+      ss ? tc::CHAIN_SS : 0, B, forced == nullptr ? 1 : 0);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -692,6 +691,7 @@ __global__ void decode_init_kernel(int64_t* tokens, int ld, uint8_t* finished, f
       st->done = max_length <= 1 ? 1 : 0;
       st->final_len = max_length <= 1 ? 1 : max_length;
       st->unfinished = 0;
+      st->blocks_done = 0;
       st->max_length = max_length;
     }
   }

@@ -47,7 +47,8 @@ struct DecState {
   int final_len;    // output length (HF dynamic length), valid when done
   int unfinished;   // rows still unfinished after the current step (accumulated by atomics)
   int max_length;   // length cap
-  int pad_[3];
+  int blocks_done;  // select_token_kernel blocks that finished the current step (the last one advances the state)
+  int pad_[2];
 };
 
 // ---- conversions ---------------------------------------------------------------------------

@@ -413,65 +413,84 @@ __device__ __forceinline__ void embed_row(const float* __restrict__ src, float* 
 }
 
 // ------------------------------------------------------------------ greedy selection (a9)
-// One block per row: argmax (lowest index wins ties, NaN counts as max like torch.argmax),
-// pad-if-finished, EOS bookkeeping, optional teacher forcing, next-step embedding gather.
-__global__ void __launch_bounds__(128) select_token_kernel(const float* __restrict__ logits, int V,
-                                                           int64_t* __restrict__ tokens, int ld_tok,
-                                                           const int64_t* __restrict__ forced,
-                                                           uint8_t* __restrict__ finished,
-                                                           const float* __restrict__ table, float* __restrict__ x, int D,
-                                                           float* __restrict__ logits_out, DecState* __restrict__ st,
-                                                           int pad_id, int eos_id, bf16* __restrict__ xb,
-                                                           float* __restrict__ ss, int ss_ld) {
+// One WARP per row: argmax by shuffles (lowest index wins ties, NaN counts as max like torch.argmax), pad-if-finished,
+// EOS bookkeeping, optional teacher forcing, next-step embedding gather (+ bf16 copy and sum of squares for the decode
+// chain).  The block that finishes last also advances the decode state (step counter, "all rows finished" / length
+// cap), so the step needs no separate single-thread launch.
+constexpr int SELECT_ROWS = 8;  // rows (warps) per block
+__global__ void __launch_bounds__(32 * SELECT_ROWS) select_token_kernel(
+    const float* __restrict__ logits, int V, int64_t* __restrict__ tokens, int ld_tok, const int64_t* __restrict__ forced,
+    uint8_t* __restrict__ finished, const float* __restrict__ table, float* __restrict__ x, int D,
+    float* __restrict__ logits_out, DecState* __restrict__ st, int pad_id, int eos_id, bf16* __restrict__ xb,
+    float* __restrict__ ss, int ss_ld, int B, int greedy_stop) {
   if (st->done) return;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * SELECT_ROWS + (threadIdx.x >> 5);
   const int t = st->t;
-  const float* lr = logits + (size_t)b * V;
-  float best = 0.f;
-  int bi = 0x7fffffff;
-  for (int i = tid; i < V; i += 128) {
-    float v = lr[i];
-    if (logits_out != nullptr) logits_out[((size_t)b * (st->max_length - 1) + t) * V + i] = v;
-    if (argmax_better(v, i, best, bi)) { best = v; bi = i; }
-  }
-  __shared__ float sv[128];
-  __shared__ int si[128];
-  sv[tid] = best;
-  si[tid] = bi;
-  __syncthreads();
-  for (int s = 64; s > 0; s >>= 1) {
-    if (tid < s && argmax_better(sv[tid + s], si[tid + s], sv[tid], si[tid])) {
-      sv[tid] = sv[tid + s];
-      si[tid] = si[tid + s];
+  int unfinished = 0;
+  if (b < B) {
+    const float* lr = logits + (size_t)b * V;
+    float best = 0.f;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < V; i += 32) {
+      const float v = lr[i];
+      if (logits_out != nullptr) logits_out[((size_t)b * (st->max_length - 1) + t) * V + i] = v;
+      if (argmax_better(v, i, best, bi)) { best = v; bi = i; }
     }
-    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (argmax_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    int next = 0;
+    if (lane == 0) {
+      int fin = finished[b];
+      next = fin ? pad_id : bi;
+      if (forced != nullptr) next = (int)forced[(size_t)b * ld_tok + t + 1];
+      tokens[(size_t)b * ld_tok + t + 1] = next;
+      if (next == eos_id) fin = 1;
+      finished[b] = (uint8_t)fin;
+      unfinished = fin ? 0 : 1;
+    }
+    next = __shfl_sync(0xffffffffu, next, 0);
+    next = next < 0 ? 0 : (next >= V ? V - 1 : next);
+    // embedding row -> residual stream (+ bf16 copy, sum of squares in ss[0], zeros in ss[1..])
+    const float4* src = reinterpret_cast<const float4*>(table + (size_t)next * D);
+    float part = 0.f;
+    for (int i = lane; i < D / 4; i += 32) {
+      const float4 v = src[i];
+      reinterpret_cast<float4*>(x + (size_t)b * D)[i] = v;
+      if (xb != nullptr) {
+        const float o[4] = {v.x, v.y, v.z, v.w};
+        store4(xb + (size_t)b * D + 4 * i, o);
+      }
+      part += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (ss != nullptr) {
+      part = warp_sum(part);
+      if (lane < ss_ld) ss[(size_t)b * ss_ld + lane] = lane == 0 ? part : 0.f;
+    }
   }
-  __shared__ int s_next;
-  if (tid == 0) {
-    int fin = finished[b];
-    int next = fin ? pad_id : si[0];
-    if (forced != nullptr) next = (int)forced[(size_t)b * ld_tok + t + 1];
-    tokens[(size_t)b * ld_tok + t + 1] = next;
-    if (next == eos_id) fin = 1;
-    finished[b] = (uint8_t)fin;
-    if (!fin) atomicAdd(&st->unfinished, 1);
-    s_next = next < 0 ? 0 : (next >= V ? V - 1 : next);
+  // block tally, then the last block to finish advances the step
+  const int block_unfinished = __syncthreads_count(unfinished);
+  if (threadIdx.x == 0) {
+    if (block_unfinished) atomicAdd(&st->unfinished, block_unfinished);
+    __threadfence();
+    const int ticket = atomicAdd(&st->blocks_done, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      __threadfence();
+      const int left = atomicAdd(&st->unfinished, 0);
+      const int tn = t + 1;  // tokens generated so far (excluding BOS) -> sequence length tn + 1
+      st->unfinished = 0;
+      st->blocks_done = 0;
+      if ((greedy_stop && left == 0) || tn + 1 >= st->max_length) {
+        st->final_len = tn + 1;
+        st->done = 1;
+      }
+      st->t = tn;
+    }
   }
-  __syncthreads();
-  embed_row(table + (size_t)s_next * D, x + (size_t)b * D, xb ? xb + (size_t)b * D : nullptr,
-            ss ? ss + (size_t)b * ss_ld : nullptr, ss_ld, D);
-}
-
-// advances the step counter; detects "all rows finished" / length cap.  <<<1,1>>>
-__global__ void step_advance_kernel(DecState* st, int greedy_stop) {
-  if (st->done) return;
-  int t = st->t + 1;  // tokens generated so far = t (excluding BOS) -> sequence length t + 1
-  st->t = t;
-  if ((greedy_stop && st->unfinished == 0) || t + 1 >= st->max_length) {
-    st->done = 1;
-    st->final_len = t + 1;
-  }
-  st->unfinished = 0;
 }
 
 // ------------------------------------------------------------------ framing + window + even/odd fold + 3-way bf16 split (a3)
