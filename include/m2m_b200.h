@@ -41,7 +41,8 @@ typedef enum m2m_status {
 } m2m_status;
 
 typedef enum m2m_precision {
-  M2M_FP32 = 0, /* parity mode: fp32 weights, activations, KV cache, CUDA-core FMA GEMMs */
+  M2M_FP32 = 0, /* parity mode: fp32 weights, activations and KV cache; GEMMs as fp32-class three-term bf16 split
+                   products on the tensor cores (or CUDA-core FFMA, flag bit9) */
   M2M_BF16 = 1  /* throughput mode: bf16 weights / GEMM operands / KV cache, fp32 accumulate,
                    fp32 residual stream, softmax and norms */
 } m2m_precision;
@@ -192,7 +193,8 @@ int m2m_stats_get(m2m_ctx* ctx, m2m_stats* out);
  * bit6 = use the CUDA-core sequence attention instead of the fused tcgen05 encoder attention,
  * bit7 = bf16 contexts: run the decode step as separate RMSNorm / GEMM launches instead of the cluster-phased
  * tcgen05 GEMM chain (A/B testing), bit8 = prefill GEMMs on the one-tile-per-CTA tcgen05 kernel instead of the
- * persistent one (A/B testing). */
+ * persistent one (A/B testing), bit9 = fp32 contexts: GEMMs on the CUDA-core FFMA kernel instead of the tcgen05
+ * three-term split-product kernel (A/B testing). */
 int m2m_set_flags(m2m_ctx* ctx, uint32_t flags);
 
 /* Test hook (tests/test_gpu_gemm.py): d_C fp32 [M,N] = A[M,K] . W[N,K]^T with bf16 device operands, through

@@ -126,6 +126,9 @@ struct m2m_ctx {
   // folded DFT tables [n_fft/2 frequencies][n_fft/2 samples n = 1..n_fft/2]: fp32 cos | sin (dft_basis = cos,
   // dft_basis + H*H = sin) and their hi/mid/lo bf16 terms [3][H][H] for the tcgen05 path
   bf16 *dft_cos3 = nullptr, *dft_sin3 = nullptr;
+  // fp32 contexts: fp32 weight pointer -> its three-term bf16 split [3][N*K] (tcgen05 split-product GEMMs)
+  std::map<const void*, const bf16*> w3_of;
+  DevBuf split_scratch;  // [3][M][K] bf16 split of the current GEMM's fp32 A operand
 
   // workspaces
   int64_t generation = 0;
@@ -242,6 +245,35 @@ static int gemm(m2m_ctx* c, const T* A, int lda, const T* W, int M, int N, int K
       return 0;
     }
   }
+  if constexpr (std::is_same<T, float>::value) {
+    // fp32 parity mode on the tensor cores: A is split into three bf16 terms on the fly, W was split at load time, the
+    // six significant products are accumulated in fp32 TMEM (leading and cross terms in separate accumulators): the
+    // result is fp32-class (tests: tokens identical to the reference), at several times the FFMA rate
+    auto w3 = c->w3_of.find(W);
+    if (!(c->flags & (8u | 512u)) && w3 != c->w3_of.end() && tc::supported(M, N, K, lda)) {
+      const size_t need = (size_t)3 * M * K * sizeof(bf16);
+      if (need > c->split_scratch.cap) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &cs);
+        M2M_REQUIRE(cs == cudaStreamCaptureStatusNone, "internal: split scratch must be sized before graph capture");
+        M2M_TRY(c->split_scratch.ensure(need, &c->generation));
+      }
+      bf16* a3 = c->split_scratch.as<bf16>();
+      const size_t total = (size_t)M * (K / 8);
+      split3_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16), 256, 0, s>>>(
+          A, lda, a3, (size_t)M, K, (size_t)M * K, st);
+      LAUNCH_CHECK(c);
+      const long tiles128 = (long)((M + tc::BM - 1) / tc::BM) * ((N + 127) / 128);
+      e = tiles128 >= c->num_sms ? tc::launch_cfg<128, 2, Epi, 3>(a3, K, w3->second, M, N, K, epi, st, s, M, N)
+                                 : tc::launch_cfg<64, 3, Epi, 3>(a3, K, w3->second, M, N, K, epi, st, s, M, N);
+      if (e != cudaSuccess) {
+        set_error("tcgen05 split-product gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
+        return M2M_ERR_CUDA;
+      }
+      c->stats.kernel_launches++;
+      return 0;
+    }
+  }
   e = launch_gemm_simt(RowMajorA<T>{A, lda}, W, K, M, N, K, epi, st, s, c->num_sms);
   if (e != cudaSuccess) {
     set_error("gemm launch failed (M=%d N=%d K=%d): %s", M, N, K, cudaGetErrorString(e));
@@ -282,9 +314,10 @@ static int seq_attn(m2m_ctx* c, const T* Q, int ldq, const T* K, const T* V, siz
 //            (six bf16 products per fp32 product into one fp32 TMEM accumulator; EpiDftRe, then EpiDftPower)
 //   fp32   : 2 x gemm_simt_kernel<FoldA, ...> (halves built on the fly, FFMA)
 static bool mel_use_tc(const m2m_ctx* c) {
+  // default in BOTH precisions: with the leading and the cross products in separate TMEM accumulators the three-term
+  // split-bf16 DFT is more accurate than the FFMA one (1.2e-5 vs 2.0e-5 normalised error on noise) and 4x faster
   if (c->flags & 16u) return false;
-  if (c->flags & 32u) return true;
-  return c->cfg.precision == M2M_BF16;
+  return true;
 }
 
 static int logmel_impl(m2m_ctx* c, const float* d_wave, int B, int S, float* d_mel, cudaStream_t s) {
@@ -734,6 +767,8 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   M2M_TRY(c->dec_finished.ensure((size_t)B, &c->generation));
   M2M_TRY(c->dec_tokens.ensure((size_t)B * max_length * sizeof(int64_t), &c->generation));
   M2M_TRY(c->dec_state.ensure(sizeof(DecState), &c->generation));
+  if (std::is_same<T, float>::value && !c->w3_of.empty())  // largest decode-step A operand: gg [B, d_ff]
+    M2M_TRY(c->split_scratch.ensure((size_t)3 * B * std::max(F, I) * sizeof(bf16), &c->generation));
 
   const int n_steps = max_length - 1;
   const bool timing = c->timing_on;
@@ -970,8 +1005,30 @@ struct ArenaBuilder {
   }
   size_t push_f32(const std::vector<float>& v) { return push_bytes(v.data(), v.size() * 4); }
   size_t push_i32(const std::vector<int>& v) { return push_bytes(v.data(), v.size() * 4); }
+  // fp32 contexts: every GEMM weight also gets its three-term bf16 split (x = hi + mid + lo, 24 mantissa bits), stacked
+  // [3][numel], for the tcgen05 split-product GEMM; (fp32 offset, split offset) pairs are resolved after the upload
+  bool want_split3 = false;
+  std::vector<std::pair<size_t, size_t>> split_pairs;
+  size_t push_split3(const std::vector<float>& v) {
+    auto bf2f = [](uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; };
+    std::vector<uint16_t> h3(3 * v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+      const uint16_t hi = f2bf(v[i]);
+      const float r1 = v[i] - bf2f(hi);  // exact
+      const uint16_t mid = f2bf(r1);
+      const float r2 = r1 - bf2f(mid);   // exact
+      h3[i] = hi;
+      h3[v.size() + i] = mid;
+      h3[2 * v.size() + i] = f2bf(r2);
+    }
+    return push_bytes(h3.data(), h3.size() * 2);
+  }
   size_t push_typed(const std::vector<float>& v, bool as_bf16) {
-    if (!as_bf16) return push_f32(v);
+    if (!as_bf16) {
+      const size_t off = push_f32(v);
+      if (want_split3) split_pairs.emplace_back(off, push_split3(v));
+      return off;
+    }
     std::vector<uint16_t> h(v.size());
     for (size_t i = 0; i < v.size(); ++i) h[i] = f2bf(v[i]);
     return push_bytes(h.data(), h.size() * 2);
@@ -1119,7 +1176,7 @@ int m2m_ctx_destroy(m2m_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   DevBuf* bufs[] = {&c->arena, &c->mel_power, &c->mel_a3, &c->mel_y0, &c->embeds, &c->enc_x, &c->enc_h, &c->enc_qkv, &c->enc_ao, &c->enc_g,
                     &c->enc_out, &c->ckv, &c->skv, &c->dec_xb, &c->dec_x, &c->dec_h, &c->dec_q, &c->dec_ao, &c->dec_g,
-                    &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->dec_ss, &c->chain_trace, &c->tf_x, &c->tf_h,
+                    &c->dec_logits, &c->dec_finished, &c->dec_tokens, &c->dec_state, &c->dec_err, &c->dec_ss, &c->chain_trace, &c->split_scratch, &c->tf_x, &c->tf_h,
                     &c->tf_qkv, &c->tf_ao, &c->tf_g, &c->tf_q, &c->host_wave[0], &c->host_wave[1], &c->host_cond[0],
                     &c->host_cond[1], &c->host_tokens, &c->host_tok16};
   for (DevBuf* b : bufs) b->release();
@@ -1170,6 +1227,7 @@ int m2m_finalize_weights(m2m_ctx* c) {
   const bool bf = g.precision == M2M_BF16;
   if (c->enc_lut.empty() || c->dec_lut.empty()) { set_error("finalize: bucket LUTs were never set"); return M2M_ERR_STATE; }
   ArenaBuilder ab;
+  ab.want_split3 = !bf;
   struct EncOff { size_t ln0, ln1, wqkv, wo, wi, wffo; };
   struct DecOff { size_t ln0, ln1, ln2, wqkv, wo, wcq, wckv, wco, wi, wffo, wqkv_ln, wcq_ln, wi_ln; };
   std::vector<EncOff> eo(g.n_layers);
@@ -1374,6 +1432,8 @@ int m2m_finalize_weights(m2m_ctx* c) {
   M2M_CUDA(cudaMemcpy(c->arena.p, ab.host.data(), ab.host.size(), cudaMemcpyHostToDevice));
   uint8_t* base = c->arena.as<uint8_t>();
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  c->w3_of.clear();
+  for (auto& pr : ab.split_pairs) c->w3_of[base + pr.first] = reinterpret_cast<const bf16*>(base + pr.second);
   c->enc.resize(g.n_layers);
   c->dec.resize(g.n_layers);
   for (int l = 0; l < g.n_layers && has_model; ++l) {

@@ -5,10 +5,11 @@
 //              128B-swizzled shared memory (one tensor map, 64-row boxes)
 //   warp 1   : MMA — S = Q K^T (tcgen05.mma, M=128, N=NK, K=64) into TMEM; later O = P V (M=128, N=64, K=NK,
 //              V consumed as an MN-major B operand straight from its [key][d] layout)
-//   warps 2-5: softmax — each thread owns one query row: tcgen05.ld the scores, add the relative-position
-//              bias from the LUT, row max / exp / sum in registers (no cross-thread reduction at all),
-//              write P as bf16 into the swizzled A-operand layout, fence to the async proxy, signal warp 1;
-//              finally tcgen05.ld O, scale by 1/sum, store bf16.
+//   warps 2-9: softmax — two warps per TMEM lane quarter, each takes half of the key chunks of its 32 query rows
+//              (the kernel is bound by the latency of this stage): tcgen05.ld the scores, add the relative-position
+//              bias from the LUT, row max / exp / sum in registers, the two halves exchange max and sum once each
+//              through shared memory; write P as bf16 into the swizzled A-operand layout, fence to the async proxy,
+//              signal warp 1; finally tcgen05.ld O (32 of the 64 columns per warp), scale by 1/sum, store bf16.
 // T5 attention has no 1/sqrt(d) scaling.  Keys beyond L (tile padding) get probability 0.
 #pragma once
 
@@ -23,7 +24,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32
          (1ull << 46) | (2ull << 61);
 }
 
-__global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int L, int inner,
+constexpr int ATTN_THREADS = 32 * (2 + 8);  // TMA warp, MMA warp, eight softmax warps
+__global__ void __launch_bounds__(ATTN_THREADS) enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int L, int inner,
                                                           bf16* __restrict__ O, int ldo,
                                                           const float* __restrict__ bias, int bias_ld, int bias_zero,
                                                           int nkb, int NK, uint32_t tmem_cols) {
@@ -38,6 +40,7 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
   uint8_t* sV = smem + region_a;         // nkb boxes x 8 KB
   __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, bar_p, bar_o;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float xch[2][2][128];  // [max | sum][column half][row]: exchanged between the two warps of a quarter
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
     mbar_init(&bar_qk, 1);
     mbar_init(&bar_v, 1);
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_p, 128);
+    mbar_init(&bar_p, 256);
     mbar_init(&bar_o, 1);
     mbar_fence_init();
   }
@@ -97,16 +100,19 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
       umma_commit(&bar_o);
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3, hsel = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row of the tile == TMEM lane
     const int i = q0 + r;         // query position
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float* brow = bias + (size_t)h * bias_ld + bias_zero - i;  // brow[j] = bias[h][(j - i) + zero]
+    // this warp's key chunks: the first or the second half of the 32-column chunks
+    const int nch = (NK + 31) >> 5, hch = (nch + 1) >> 1;
+    const int cb = hsel ? hch * 32 : 0, ce = hsel ? NK : min(NK, hch * 32);
     mbar_wait(&bar_s, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int c0 = 0; c0 < NK; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
       const float* bp = brow + c0;
@@ -119,11 +125,14 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
           if (c0 + jj < L) mx = fmaxf(mx, __uint_as_float(v[jj]) + __ldg(bp + jj));
       }
     }
+    xch[0][hsel][r] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(mx, xch[0][hsel ^ 1][r]);
     float sum = 0.f;
     const int rs = r & 7;
     uint8_t* prow = sP + (size_t)(r >> 3) * 1024 + (size_t)rs * 128;
 #pragma unroll 1
-    for (int c0 = 0; c0 < NK; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
       float p[32];
@@ -141,22 +150,25 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
           sum += p[jj];
         }
       }
-      // 4 chunks of 8 keys -> 16-byte swizzled stores into k-block (c0 / 64)
+      // 4 chunks of 8 keys -> 16-byte swizzled stores into k-block (c0 / 64); columns beyond NK are never read by the MMA
       uint8_t* pk = prow + (size_t)(c0 >> 6) * 16384;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int chunk = ((c0 & 63) >> 3) + ch;  // 16-byte chunk index inside the 128-byte row
-        Vec16<bf16>::store(reinterpret_cast<bf16*>(pk + ((chunk ^ rs) << 4)), p + 8 * ch);
+        if (c0 + 8 * ch < NK) Vec16<bf16>::store(reinterpret_cast<bf16*>(pk + ((chunk ^ rs) << 4)), p + 8 * ch);
       }
     }
+    xch[1][hsel][r] = sum;
     // P (generic-proxy writes) must be visible to the tensor core (async proxy) before the PV MMAs
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(&bar_p);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum += xch[1][hsel ^ 1][r];
     mbar_wait(&bar_o, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = 1.f / sum;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    {
+      const int c0 = hsel * 32;  // each warp of the quarter stores half of the 64 output columns
       uint32_t v[32];
       tmem_ld32(tmem_o + lane_addr + (uint32_t)c0, v);
       if (i < L) {
@@ -184,11 +196,13 @@ __global__ void __launch_bounds__(192) enc_attn_tc_kernel(const __grid_constant_
 // processed in tiles of 128.  Two passes over the key tiles avoid any rescaling of the TMEM accumulator:
 //   pass 1: S = Q K_t^T (tensor core) -> row max of (S + bias) under the causal mask            (no exp, no V)
 //   pass 2: S again, P = exp(S + bias - max) as bf16 into the swizzled A-operand layout, O += P V_t in TMEM
+// Eight softmax warps (two per TMEM lane quarter, 64 key columns of each tile per warp) share the latency-bound
+// tcgen05.ld / bias / exp stage; the halves exchange the row max after pass 1 and the row sum at the end.
 // The second QK^T costs 1/3 more tensor work on an otherwise idle pipe and removes the flash-attention
 // correction step.  Q/K/V tiles arrive by TMA (2-stage rings), every mbarrier wait is bounded.
 //   element (b, row, h, d) of Q at Q[(b*Lq + row)*ldq + h*64 + d] (tensor map tmQ, box 64x64)
 //   K/V: 2-D tensor maps over [rows_kv, ld_kv] with the (b, h) tile at column kv_col0 + h*64, row kv_row0(b) + j
-__global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(ATTN_THREADS) seq_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                           const __grid_constant__ CUtensorMap tmK,
                                                           const __grid_constant__ CUtensorMap tmV, int Lq, int Lk,
                                                           int k_col0, int v_col0, int k_head_cols, int kv_rows_per_b,
@@ -204,6 +218,7 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
   __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, s_empty, p_full, p_empty,
       o_full;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float xch[2][2][128];  // [max | sum][column half][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -220,8 +235,8 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
     mbar_init(&v_full, 1);
     mbar_init(&v_empty, 1);
     mbar_init(&s_full, 1);
-    mbar_init(&s_empty, 128);
-    mbar_init(&p_full, 128);
+    mbar_init(&s_empty, 256);
+    mbar_init(&p_full, 256);
     mbar_init(&p_empty, 1);
     mbar_init(&o_full, 1);
     mbar_fence_init();
@@ -292,7 +307,8 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
       }
     }
   } else {
-    const int q = warp & 3;
+    // two warps per TMEM lane quarter: each takes 64 of the 128 key columns of every tile (one P k-block)
+    const int q = warp & 3, hsel = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int i = q0 + r;  // query position
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -308,7 +324,7 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (it < nkt) {  // pass 1: row max
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = hsel * 64; c0 < hsel * 64 + 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
           const int jb = kt * 128 + c0;
@@ -331,11 +347,16 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&s_empty);
+        if (it == nkt - 1) {  // the two column halves of a row agree on the maximum before any exponential
+          xch[0][hsel][r] = mx;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mx = fmaxf(mx, xch[0][hsel ^ 1][r]);
+        }
       } else {  // pass 2: probabilities
         const int vi = it - nkt;
         mbar_wait(&p_empty, (vi & 1) ^ 1);  // previous PV MMAs have consumed P
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = hsel * 64; c0 < hsel * 64 + 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_s + lane_addr + (uint32_t)c0, v);
           float pbuf[32];
@@ -376,11 +397,14 @@ __global__ void __launch_bounds__(192) seq_attn_tc_kernel(const __grid_constant_
         mbar_arrive(&s_empty);
       }
     }
+    xch[1][hsel][r] = sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum += xch[1][hsel ^ 1][r];
     mbar_wait(&o_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = 1.f / sum;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    {
+      const int c0 = hsel * 32;  // each warp of the quarter stores half of the 64 output columns
       uint32_t v[32];
       tmem_ld32(tmem_o + lane_addr + (uint32_t)c0, v);
       if (i < Lq) {
@@ -431,7 +455,7 @@ inline cudaError_t launch_seq_attn(const bf16* Q, int ldq, int B, int Lq, int H,
   cudaError_t ae = ensure_smem_attr(reinterpret_cast<const void*>(seq_attn_tc_kernel), smem);
   if (ae != cudaSuccess) return ae;
   dim3 grid((Lq + 127) / 128, H, B);
-  seq_attn_tc_kernel<<<grid, 192, smem, stream>>>(tq, tk, tv, Lq, Lk, k_col0, v_col0, head_cols, rows_per_b, rows_per_h, O,
+  seq_attn_tc_kernel<<<grid, ATTN_THREADS, smem, stream>>>(tq, tk, tv, Lq, Lk, k_col0, v_col0, head_cols, rows_per_b, rows_per_h, O,
                                                   ldo, bias, bias_ld, bias_zero, causal ? 1 : 0);
   return cudaGetLastError();
 }
@@ -460,7 +484,7 @@ inline cudaError_t launch_enc_attn(const bf16* qkv, int ld, int B, int L, int H,
   cudaError_t ae = ensure_smem_attr(reinterpret_cast<const void*>(enc_attn_tc_kernel), smem);
   if (ae != cudaSuccess) return ae;
   dim3 grid((L + 127) / 128, H, B);
-  enc_attn_tc_kernel<<<grid, 192, smem, stream>>>(tm, L, H * 64, O, ldo, bias, bias_ld, bias_zero, nkb, NK, tmem_cols);
+  enc_attn_tc_kernel<<<grid, ATTN_THREADS, smem, stream>>>(tm, L, H * 64, O, ldo, bias, bias_ld, bias_zero, nkb, NK, tmem_cols);
   return cudaGetLastError();
 }
 

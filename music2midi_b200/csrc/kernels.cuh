@@ -659,6 +659,37 @@ __global__ void __launch_bounds__(512) mel_band_log_kernel(const float* __restri
   }
 }
 
+// fp32 [rows, K] (leading dimension lda) -> three bf16 terms [3][rows][K]:  x = hi + mid + lo  (24 mantissa bits).
+// The A operand of the tcgen05 split-product GEMM in fp32 contexts.  8 elements per thread, 16-byte stores.
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ A, int lda, bf16* __restrict__ out,
+                                                     size_t rows, int K, size_t split_stride,
+                                                     const DecState* __restrict__ st) {
+  if (st != nullptr && st->done) return;
+  const int chunks = K / 8;
+  const size_t total = rows * chunks;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / chunks;
+    const int k0 = (int)(i - r * chunks) * 8;
+    float x[8];
+    load4(A + r * lda + k0, x);
+    load4(A + r * lda + k0 + 4, x + 4);
+    float hi[8], mid[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float h = __bfloat162float(__float2bfloat16_rn(x[e]));
+      const float r1 = x[e] - h;
+      const float md = __bfloat162float(__float2bfloat16_rn(r1));
+      hi[e] = h;
+      mid[e] = md;
+      lo[e] = r1 - md;
+    }
+    bf16* dst = out + r * K + k0;
+    Vec16<bf16>::store(dst, hi);
+    Vec16<bf16>::store(dst + split_stride, mid);
+    Vec16<bf16>::store(dst + 2 * split_stride, lo);
+  }
+}
+
 // int64 token ids -> int16 (vocabulary 400): the host read-back moves a quarter of the bytes
 __global__ void narrow_tokens_kernel(const int64_t* __restrict__ in, int16_t* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

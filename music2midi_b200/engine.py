@@ -215,12 +215,13 @@ class Engine:
     # ------------------------------------------------------------------ introspection
     def set_flags(self, graph: bool = True, time_classes: bool = False, skip_finished: bool = True,
                   no_tensor_cores: bool = False, mel: str = "auto", no_tc_attention: bool = False,
-                  no_chain: bool = False, no_persistent_gemm: bool = False):
-        """mel: "auto" (tcgen05 DFT in bf16 contexts, fp32 CUDA-core DFT in fp32 contexts), "simt" or "tc".
+                  no_chain: bool = False, no_persistent_gemm: bool = False, no_f32_tc: bool = False):
+        """mel: "auto" / "tc" (tcgen05 three-term split DFT, both precisions) or "simt" (fp32 CUDA-core DFT).
+        no_f32_tc: fp32 contexts run their GEMMs on the CUDA-core FFMA kernel instead of the tcgen05 split-product one.
         time_classes: instrumented pass (CUDA events around every launch group, summed per kernel class).
         no_chain: bf16 contexts run the decode step as separate RMSNorm / GEMM launches (A/B testing)."""
         f = (1 if graph else 0) | (2 if time_classes else 0) | (4 if skip_finished else 0) | (8 if no_tensor_cores else 0)
-        f |= {"auto": 0, "simt": 16, "tc": 32}[mel] | (64 if no_tc_attention else 0) | (128 if no_chain else 0) | (256 if no_persistent_gemm else 0)
+        f |= {"auto": 0, "simt": 16, "tc": 32}[mel] | (64 if no_tc_attention else 0) | (128 if no_chain else 0) | (256 if no_persistent_gemm else 0) | (512 if no_f32_tc else 0)
         check(self.lib.m2m_set_flags(self._ctx, f))
 
     def stats(self, reset: bool = False) -> Dict[str, float]:

@@ -148,6 +148,13 @@ class Music2MIDI(nn.Module):
             rows += [*tokens]
         return rows
 
+    def _pinned_stage(self, n_floats: int) -> torch.Tensor:
+        buf = getattr(self, "_stage_buf", None)
+        if buf is None or buf.numel() < n_floats:
+            buf = torch.empty(n_floats, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+            self._stage_buf = buf
+        return buf[:n_floats]
+
     @torch.no_grad()
     def generate_many(self, audios, cond_index: Optional[List[int]] = None, distributed: bool = False):
         """Batch entry point (not in the reference, which transcribes one recording per call): transcribes a list
@@ -160,28 +167,26 @@ class Music2MIDI(nn.Module):
         sr = self.config.model.sample_rate
         dur = self.config.dataset.segment_duration
         split = int(sr * dur)
-        counts, padded = [], []
-        for y in audios:
-            y = np.asarray(y, dtype=np.float32)
-            n = max(1, int(np.ceil(len(y) / split)))
-            padded.append(np.pad(y, (0, n * split - len(y)), "constant"))
-            counts.append(n)
-        if not padded:
+        clips = [np.asarray(y, dtype=np.float32).reshape(-1) for y in audios]
+        counts = [max(1, -(-len(y) // split)) for y in clips]
+        if not clips:
             return []
-        lo_clip, hi_clip = 0, len(padded)
+        lo_clip, hi_clip = 0, len(clips)
         if distributed and torch.distributed.is_initialized():
-            lo_clip, hi_clip = dist_mod.shard_range(len(padded), torch.distributed.get_rank(),
+            lo_clip, hi_clip = dist_mod.shard_range(len(clips), torch.distributed.get_rank(),
                                                     torch.distributed.get_world_size())
-        local = padded[lo_clip:hi_clip]
+        local = clips[lo_clip:hi_clip]
         n_local = sum(counts[lo_clip:hi_clip])
         if local:
-            # one pinned staging buffer for all local segments, then the host-buffer entry point of the library: the
-            # upload of device batch i + 1 overlaps the decode of batch i, tokens come back as int16 (m2m_transcribe_host)
-            stage = torch.empty(n_local, split, dtype=torch.float32, pin_memory=True)
+            # one pinned staging buffer for all local segments (kept between calls: page-locking half a gigabyte costs
+            # more than the upload), zero-padded per clip in place, then the host-buffer entry point of the library:
+            # the upload of device batch i + 1 overlaps the decode of batch i, tokens come back as int16
+            stage = self._pinned_stage(n_local * split).view(n_local, split)
             flat, pos = stage.view(-1).numpy(), 0
-            for y in local:
+            for y, n in zip(local, counts[lo_clip:hi_clip]):
                 flat[pos:pos + len(y)] = y
-                pos += len(y)
+                flat[pos + len(y):pos + n * split] = 0.0
+                pos += n * split
             n_embeds = len(self.model.conditioning.embeds)
             cond = np.zeros((n_local, n_embeds), dtype=np.int64)
             if cond_index is not None:
@@ -194,7 +199,7 @@ class Music2MIDI(nn.Module):
             tok = torch.zeros(0, 1024, dtype=torch.int64)
         if distributed and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
-            rows = [sum(counts[slice(*dist_mod.shard_range(len(padded), r, world))]) for r in range(world)]
+            rows = [sum(counts[slice(*dist_mod.shard_range(len(clips), r, world))]) for r in range(world)]
             tok = dist_mod.gather_tokens(tok.to(self.device), sum(counts), counts=rows)
         tok = tok.to(torch.int64).cpu()
         out, pos = [], 0

@@ -67,3 +67,24 @@ def test_two_contexts_on_two_devices_in_one_process(state_dict):
         outs.append(eng.generate(wave.to(f"cuda:{d}"), cond.to(f"cuda:{d}"), 24).cpu())
         eng.close()
     assert torch.equal(outs[0], outs[1])
+
+
+def test_fp32_split_product_gemms_match_cuda_core_gemms(engine_fp32, report):
+    """fp32 parity mode runs its GEMMs as three-term bf16 split products on tcgen05 (six products, fp32 accumulate);
+    against the plain FFMA kernels on the same weights the logits agree to fp32 rounding noise and the greedy tokens
+    are identical."""
+    from music2midi_b200 import synthetic as syn
+
+    wave = syn.audio_noise(4, 78).to(DEV)
+    cond = torch.zeros(4, 2, dtype=torch.long, device=DEV)
+    emb = engine_fp32.condition(engine_fp32.logmel(wave), cond)
+    toks, lg = engine_fp32.generate_from_embeds(emb, 64, return_logits=True)
+    engine_fp32.set_flags(no_f32_tc=True)
+    try:
+        toks2, lg2 = engine_fp32.generate_from_embeds(emb, 64, return_logits=True)
+    finally:
+        engine_fp32.set_flags(no_f32_tc=False)
+    assert torch.equal(toks, toks2)
+    d = float((lg - lg2).abs().max())
+    report(test="fp32_tc_vs_simt_logits", max_abs=d)
+    assert d <= 5e-4

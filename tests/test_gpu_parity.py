@@ -99,15 +99,21 @@ def test_logmel_leading_dims_and_empty(engine_fp32):
 
 
 def test_logmel_frontend_is_fp32_class_in_both_engines(engine_fp32, engine_bf16):
-    """The bf16 engine keeps an fp32-accurate frontend (split-bf16 DFT on tcgen05): same tolerance."""
+    """Both engines run the same frontend (split-bf16 DFT on tcgen05, the more accurate of the two paths; the FFMA
+    one stays selectable): identical bits between the engines on either path, same tolerance against the reference."""
     w = syn.audio_noise(2, 6)
     ref = port.logmel(w, syn.hann_window(), syn.mel_filterbank())
-    for eng in (engine_fp32, engine_bf16):
-        assert norm_err(eng.logmel(w.to(DEV)), ref) <= MEL_TOL_NOISE
-    engine_bf16.set_flags(mel="simt")
-    a = engine_bf16.logmel(w.to(DEV))
-    engine_bf16.set_flags()
-    assert torch.equal(a, engine_fp32.logmel(w.to(DEV)))
+    outs = {}
+    for path in ("auto", "simt"):
+        for name, eng in (("fp32", engine_fp32), ("bf16", engine_bf16)):
+            eng.set_flags(mel=path)
+            try:
+                outs[path, name] = eng.logmel(w.to(DEV))
+            finally:
+                eng.set_flags()
+            assert norm_err(outs[path, name], ref) <= MEL_TOL_NOISE
+        assert torch.equal(outs[path, "fp32"], outs[path, "bf16"])
+    assert not torch.equal(outs["auto", "fp32"], outs["simt", "fp32"])  # the switch really selects another kernel
 
 
 # ------------------------------------------------------------------------------ conditioning
