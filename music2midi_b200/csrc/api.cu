@@ -212,6 +212,9 @@ static void timing_begin(m2m_ctx* c) {
 // launches after the stop condition) are ignored
 static void timing_collect(m2m_ctx* c, int executed_steps) {
   if (!c->timing_on) return;
+  // M2M_TIMING_DUMP=<path>: one "class,step,ms" line per timed launch group (tools/profile_classes.py --per-step)
+  const char* dump_path = getenv("M2M_TIMING_DUMP");
+  FILE* dump = (dump_path && *dump_path) ? fopen(dump_path, "a") : nullptr;
   for (size_t i = 0; i < c->ev_tag.size(); ++i) {
     const int cls = c->ev_tag[i] & 0xff, step = c->ev_tag[i] >> 8;
     if (cls >= KC_DEC_SELF_ATTN && step >= executed_steps) continue;
@@ -219,7 +222,9 @@ static void timing_collect(m2m_ctx* c, int executed_steps) {
     if (cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]) != cudaSuccess) continue;
     c->stats.class_ms[cls] += ms;
     c->stats.class_launches[cls] += 1;
+    if (dump) fprintf(dump, "%d,%d,%.6f\n", cls, step, ms);
   }
+  if (dump) fclose(dump);
   c->timing_on = false;
 }
 
