@@ -455,9 +455,15 @@ static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d
   for (int l = 0; l < g.n_layers; ++l) {
     const EncLayerW& w = c->enc[l];
     M2M_TRY(norm(w.ln0, h));
+    // bf16, L <= 256: fused tcgen05 attention with all keys in one tile; it reads Q/K/V head-major
+    bool fused_attn = false;
+    if constexpr (std::is_same<T, bf16>::value) fused_attn = !(c->flags & 64u) && tc::enc_attn_supported(L, I);
     {
       TimedScope ts(c, KC_ENC_GEMM, s);
-      M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
+      if (fused_attn)
+        M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiHeadMajorQKV<T>{qkv, I, L, M * I}, nullptr, s));
+      else
+        M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
     }
     {
       TimedScope ts(c, KC_ENC_ATTN, s);
@@ -465,8 +471,8 @@ static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d
       if constexpr (std::is_same<T, bf16>::value) {
         if (!(c->flags & 64u)) {
           cudaError_t e;
-          if (tc::enc_attn_supported(L, I, 3 * I))  // fused tcgen05 attention, all keys in one tile
-            e = tc::launch_enc_attn(qkv, 3 * I, B, L, g.n_heads, ao, I, c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s);
+          if (fused_attn)
+            e = tc::launch_enc_attn(qkv, B, L, g.n_heads, ao, I, c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, s, c->num_sms);
           else  // longer inputs: key-tiled kernel
             e = tc::launch_seq_attn(qkv, 3 * I, B, L, g.n_heads, qkv, qkv, (uint64_t)M, 3 * I, I, 2 * I, 64, L, 0, L, ao, I,
                                     c->enc_bias, c->enc_bias_ld, g.max_enc_len - 1, false, s);

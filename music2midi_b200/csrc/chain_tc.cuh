@@ -235,21 +235,6 @@ __device__ __forceinline__ void umma_commit_multicast_u(uint32_t bar, uint16_t m
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid_constant__ ChainParams P) {
   if (P.st != nullptr && P.st->done) return;  // uniform over the grid: finished decode, nothing to do
   extern __shared__ uint8_t smem_raw[];

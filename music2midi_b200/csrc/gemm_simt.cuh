@@ -145,6 +145,22 @@ struct EpiHeadMajorKV {
     store4(dst, val);
   }
 };
+// Encoder fused QKV, written head-major for the fused attention kernel: rows m = (b, j), cols [0,I) -> Q, [I,2I) -> K,
+// [2I,3I) -> V, element (seg, b, h, j, d) at base + ((((seg * B + b) * H + h) * L + j) * 64 + d): every (b, h) tile of
+// Q, K and V is one contiguous block (the packed [B*L, 3I] layout makes each tile 64 x 128-byte pieces 6 KB apart,
+// which costs the attention kernel most of its HBM bandwidth).
+template <typename TC>
+struct EpiHeadMajorQKV {
+  TC* base;
+  int inner, L;
+  size_t seg_stride;  // B * inner * L elements
+  __device__ __forceinline__ void operator()(int m, int n, const float val[4], const DecState*) const {
+    int seg = n / inner, c = n - seg * inner;
+    int b = m / L, j = m - b * L;
+    TC* dst = base + seg * seg_stride + ((size_t)b * (inner >> 6) + (c >> 6)) * ((size_t)L * 64) + (size_t)j * 64 + (c & 63);
+    store4(dst, val);
+  }
+};
 // Folded DFT, even half x cos table:  Re[m, f] = y0[m] + acc  (the odd half x sin table is a plain EpiStore<float>)
 struct EpiDftRe {
   float* P;

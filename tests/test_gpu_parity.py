@@ -173,6 +173,18 @@ def test_encoder_bf16(engine_bf16, cpu_embeds, oracle_weights, report):
         e = norm_err(engine_bf16.encode(xl.to(DEV)), ref)
         report(test="encoder_bf16_oracle", L=L, norm_err=e)
         assert e <= 3e-2, (L, e)
+    # more (tile, head, row) items than SMs: every CTA of the persistent attention kernel pipelines several items
+    # (three-stage ring, two TMEM accumulator pairs; one score accumulator for L > 192); against the CUDA-core attention
+    for L, B in ((190, 100), (256, 70), (100, 90), (128, 150)):
+        xl = (torch.randn(B, L, 384, generator=gen) * 3.0).to(DEV)
+        a = engine_bf16.encode(xl)
+        engine_bf16.set_flags(no_tc_attention=True)
+        b = engine_bf16.encode(xl)
+        engine_bf16.set_flags()
+        e = norm_err(a, b.cpu())
+        report(test="encoder_bf16_many_items", L=L, B=B, tc_vs_simt=e)
+        assert e <= 2e-2, (L, B, e)
+        assert torch.equal(a, engine_bf16.encode(xl))  # and run-to-run identical
 
 
 # ------------------------------------------------------------------------------ decode: logits
