@@ -461,7 +461,7 @@ static int encode_impl(m2m_ctx* c, const float* d_embeds, int B, int L, float* d
     {
       TimedScope ts(c, KC_ENC_GEMM, s);
       if (fused_attn)
-        M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiHeadMajorQKV<T>{qkv, I, L, M * I}, nullptr, s));
+        M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiHeadMajorQKV<T>{qkv, I, FastDiv((uint32_t)L), M * I}, nullptr, s));
       else
         M2M_TRY(gemm<T>(c, h, D, (const T*)w.wqkv, (int)M, 3 * I, D, EpiStore<T>{qkv, 3 * I}, nullptr, s));
     }
@@ -518,7 +518,7 @@ static int cross_kv_impl(m2m_ctx* c, const T* enc_out, int B, int L, cudaStream_
   for (int l = 0; l < g.n_layers; ++l) {
     T* dst = c->ckv.as<T>() + (size_t)l * M * 2 * I;  // [K block: B*L*I | V block: B*L*I], each [b][h][j][64]
     M2M_TRY(gemm<T>(c, enc_out, D, (const T*)c->dec[l].wckv, (int)M, 2 * I, D,
-                    EpiHeadMajorKV<T>{dst, dst + M * I, I, L}, nullptr, s));
+                    EpiHeadMajorKV<T>{dst, dst + M * I, I, FastDiv((uint32_t)L)}, nullptr, s));
   }
   return 0;
 }
