@@ -41,10 +41,22 @@ if [ "$what" = ncu ] || [ "$what" = all ]; then
       python bench.py --steps 1 --warmup 0 --max-length 64 --no-fp32 --no-extra --no-cpu-baseline --no-roofline > $out/r2_launches_step60.log 2>&1
   echo "launch list rc=$? $(wc -l < $out/r2_launches_step60.csv) lines"
 fi
-if [ "$what" = sanitize ] || [ "$what" = all ]; then
+if [ "$what" = late ]; then  # kernels that changed after the first evidence run of the round
+  cap r2_ncu_enc_attn_tc    enc_attn_tc_kernel        1  --max-length 2
+  cap r2_ncu_gemm_tc2_qkv   "gemm_tc2_kernel.*256.*EpiHeadMajorQKV" 1 --max-length 2
+  cap r2_ncu_cross_kv       "gemm_tc2_kernel.*EpiHeadMajorKV" 0 --max-length 2
+  cap r2_ncu_select_token   select_token_kernel       1  --max-length 4
+  cap r2_ncu_seq_attn_tc_self  seq_attn_tc_kernel     2  --max-length 2 --clips 8 --teacher-forced 32   # decoder layer 1, causal
+  cap r2_ncu_seq_attn_tc_cross seq_attn_tc_kernel     3  --max-length 2 --clips 8 --teacher-forced 32   # decoder layer 1, cross
+  cap r2_ncu_f32_split_gemm "gemm_tc_kernel<.int.128, .int.2, .int.3, m2m::EpiStore" 2 --max-length 2 --precision fp32 --clips 64
+  cap r2_ncu_f32_split3     split3_kernel             2  --max-length 2 --precision fp32 --clips 64
+  cap r2_ncu_f32_dec_self_attn "decode_attn_kernel<float, .bool.1" 600 --max-length 104 --precision fp32
+fi
+if [ "$what" = sanitize ] || [ "$what" = all ] || [ "$what" = late ]; then
   timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
-      -k "gemm_paths or logmel_matches or bf16_batch_sizes or encoder_bf16 or conditioning or eos_pad" > $out/r2_sanitizer_memcheck.log 2>&1
+      -k "gemm_paths or logmel_matches or bf16_batch_sizes or encoder_bf16 or conditioning or eos_pad or fp32_split_product or frontend_is_fp32" > $out/r2_sanitizer_memcheck.log 2>&1
   echo "memcheck rc=$?"; tail -4 $out/r2_sanitizer_memcheck.log
+  [ "$what" = late ] && exit 0
   timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
       -k "bf16_batch_sizes and (1 or 129)" > $out/r2_sanitizer_racecheck_chain.log 2>&1
   echo "racecheck(chain) rc=$?"; tail -4 $out/r2_sanitizer_racecheck_chain.log
