@@ -189,7 +189,7 @@ int m2m_stats_get(m2m_ctx* ctx, m2m_stats* out);
  * finished rows are not skipped), bit2 = skip finished rows in attention (default 1),
  * bit3 = route bf16 GEMMs to the CUDA-core kernel instead of tcgen05 (A/B testing),
  * bit4 = force the fp32 CUDA-core DFT in the log-mel frontend, bit5 = force the tcgen05 split-bf16 DFT
- * (default: tcgen05 in M2M_BF16 contexts, fp32 CUDA-core in M2M_FP32 contexts),
+ * (default: tcgen05 in both precisions: it is the more accurate of the two),
  * bit6 = use the CUDA-core sequence attention instead of the fused tcgen05 encoder attention,
  * bit7 = bf16 contexts: run the decode step as separate RMSNorm / GEMM launches instead of the cluster-phased
  * tcgen05 GEMM chain (A/B testing), bit8 = prefill GEMMs on the one-tile-per-CTA tcgen05 kernel instead of the
