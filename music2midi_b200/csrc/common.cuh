@@ -203,6 +203,32 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, 
       : "memory");
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2: two fp32 operations per issue slot; operands are 64-bit register pairs)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// exp2 on the SFU, denormal results flushed: one MUFU, no range fix-up (ex2(-inf) = 0)
+__device__ __forceinline__ float exp2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // gelu_new (tanh approximation), transformers NewGELUActivation
 __device__ __forceinline__ float gelu_new(float x) {
   const float k = 0.7978845608028654f;  // sqrt(2/pi)

