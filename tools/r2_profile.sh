@@ -41,6 +41,11 @@ if [ "$what" = ncu ] || [ "$what" = all ]; then
       python bench.py --steps 1 --warmup 0 --max-length 64 --no-fp32 --no-extra --no-cpu-baseline --no-roofline > $out/r2_launches_step60.log 2>&1
   echo "launch list rc=$? $(wc -l < $out/r2_launches_step60.csv) lines"
 fi
+if [ "$what" = attn ]; then  # decode attention after the packed-arithmetic change
+  cap r2_ncu_dec_self_attn  "decode_attn_kernel<__nv_bfloat16, .bool.1"  1800 --max-length 304   # layer 0 of decode step 300
+  cap r2_ncu_dec_cross_attn "decode_attn_kernel<__nv_bfloat16, .bool.0" 60   --max-length 12
+  exit 0
+fi
 if [ "$what" = late ]; then  # kernels that changed after the first evidence run of the round
   cap r2_ncu_enc_attn_tc    enc_attn_tc_kernel        1  --max-length 2
   cap r2_ncu_gemm_tc2_qkv   "gemm_tc2_kernel.*256.*EpiHeadMajorQKV" 1 --max-length 2
