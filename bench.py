@@ -509,7 +509,7 @@ def run_ours(args):
             "segments": n_mel, "frames": frames, "ms": mel_ms, "frames_per_s": frames / (mel_ms / 1e3),
             "roofline": {"bound": "tensor", "achieved": mel_tf, "peak": peaks[1], "unit": "TFLOP/s", "frac": mel_tf / peaks[1],
                          "algorithmic": "fp32 DFT-as-GEMM flops 2*T*2048*2050 per segment", "peak_kind": "burst"},
-            "path": "tcgen05 split-bf16 DFT" if args.precision == "bf16" else "fp32 CUDA-core DFT"}
+            "path": "tcgen05 split-bf16 DFT"}
 
         # BASELINE.json configs[2]: mel + encoder + teacher-forced decoder forward, batch 32, at the inference shape
         # (S = 48000, L_enc = 190) and the training shape (3 s @ 22050 Hz: S = 66150, L_enc = 261), labels 256 / 1024
