@@ -228,6 +228,15 @@ static void timing_collect(m2m_ctx* c, int executed_steps) {
   c->timing_on = false;
 }
 
+// Self-attention KV cache, chunk-major: [t / CH][b][h][t % CH][64] with CH keys per 4 KB chunk (32 in bf16, 16 in fp32)
+template <typename T>
+struct SelfCache {
+  static constexpr int CH = 4096 / (64 * (int)sizeof(T));
+  static constexpr int SHIFT = CH == 32 ? 5 : 4;
+  static size_t slab(int B, int I) { return (size_t)B * I * CH; }  // elements of one chunk index, all (row, head) pairs
+  static size_t layer(int B, int I, int Tmax) { return slab(B, I) * (size_t)((Tmax + CH - 1) / CH); }
+};
+
 // ------------------------------------------------------------------ GEMM dispatch
 // C = A[M,K] . W[N,K]^T with epilogue.  bf16 operands with large M go to the tcgen05 kernel,
 // everything else (fp32 parity mode, small M) to the CUDA-core kernel.
@@ -550,7 +559,7 @@ static int build_chain_plan(m2m_ctx* c, int B, int L, int max_length, float* log
   bf16* ao = c->dec_ao.as<bf16>();
   bf16* gg = c->dec_g.as<bf16>();
   float* ss = c->dec_ss.as<float>();
-  const size_t self_layer = (size_t)B * Tmax * I;
+  const size_t self_layer = SelfCache<bf16>::layer(B, I, Tmax);
   auto base = [&](tc::ChainParams& P, int n_phases) {
     memset(&P, 0, sizeof(P));
     P.n_phases = n_phases;
@@ -574,8 +583,10 @@ static int build_chain_plan(m2m_ctx* c, int B, int L, int max_length, float* log
     ph->out0 = q;
     ph->out1 = kc;
     ph->out2 = kc + self_layer;
-    ph->s0 = (long long)Tmax * 64;
-    ph->s1 = (long long)Tmax * I;
+    ph->s0 = (long long)SelfCache<bf16>::CH * 64;
+    ph->s1 = (long long)SelfCache<bf16>::CH * I;
+    ph->slab = (long long)SelfCache<bf16>::slab(B, I);
+    ph->t_shift = SelfCache<bf16>::SHIFT;
     ph->inner = I;
     return ok;
   };
@@ -644,17 +655,18 @@ static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const in
   uint8_t* fin = c->dec_finished.as<uint8_t>();
   int64_t* tokens = c->dec_tokens.as<int64_t>();
   const uint8_t* fin_skip = skip_finished ? fin : nullptr;
-  const size_t self_layer = (size_t)B * Tmax * I;  // elements per K (or V) per layer
+  const size_t self_layer = SelfCache<T>::layer(B, I, Tmax);  // elements per K (or V) per layer
   const size_t cross_layer = (size_t)B * L * 2 * I;
   constexpr bool FAST = !std::is_same<T, float>::value;
   dim3 agrid(g.n_heads, B);
   auto attn = [&](bool self, const T* kp, const T* vp) -> int {
     TimedScope ts(c, self ? KC_DEC_SELF_ATTN : KC_DEC_CROSS_ATTN, s, step);
     if (self)
-      decode_attn_kernel<T, true, FAST, 3><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)Tmax * I, (size_t)Tmax * 64, 0,
-                                                                 c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
+      decode_attn_kernel<T, true, FAST, 3><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)SelfCache<T>::CH * I,
+                                                                 (size_t)SelfCache<T>::CH * 64,
+                                                                 SelfCache<T>::slab(B, I) * sizeof(T), 0, c->dec_bias, g.max_positions, ao, g.n_heads, st, fin_skip);
     else
-      decode_attn_kernel<T, false, FAST, 3><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, L, nullptr, 0,
+      decode_attn_kernel<T, false, FAST, 3><<<agrid, 128, 0, s>>>(q, kp, vp, (size_t)L * I, (size_t)L * 64, 4096, L, nullptr, 0,
                                                                   ao, g.n_heads, st, fin_skip);
     LAUNCH_CHECK(c);
     return 0;
@@ -689,7 +701,8 @@ static int decode_step_launch(m2m_ctx* c, int B, int L, int max_length, const in
       M2M_TRY(chain(plan->ka[l]));
       continue;
     }
-    const EpiQKVCache<T> epi_qkv{q, kc, vc, I, (size_t)Tmax * 64, (size_t)Tmax * I};
+    const EpiQKVCache<T> epi_qkv{q, kc, vc, I, (size_t)SelfCache<T>::CH * 64, (size_t)SelfCache<T>::CH * I,
+                                 SelfCache<T>::slab(B, I), SelfCache<T>::SHIFT};
     {
       TimedScope ts(c, KC_DEC_CHAIN, s, step);
       M2M_TRY(rmsnorm<T>(c, x, w.ln0, h, B, st, s));
@@ -766,7 +779,7 @@ static int generate_from_embeds_impl(m2m_ctx* c, const float* d_embeds, int B, i
   M2M_TRY(encode_impl<T>(c, d_embeds, B, L, nullptr, true, s));
   M2M_TRY(cross_kv_impl<T>(c, c->enc_out.as<T>(), B, L, s));
 
-  M2M_TRY(c->skv.ensure((size_t)g.n_layers * 2 * B * max_length * I * sizeof(T), &c->generation));
+  M2M_TRY(c->skv.ensure((size_t)g.n_layers * 2 * SelfCache<T>::layer(B, I, max_length) * sizeof(T), &c->generation));
   M2M_TRY(c->dec_x.ensure((size_t)B * D * sizeof(float), &c->generation));
   M2M_TRY(c->dec_xb.ensure((size_t)B * D * sizeof(bf16), &c->generation));
   M2M_TRY(c->dec_ss.ensure((size_t)B * tc::CHAIN_SS * sizeof(float), &c->generation));

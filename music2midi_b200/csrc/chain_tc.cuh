@@ -77,7 +77,9 @@ struct ChainPhase {
   void* out0;       // RESIDUAL: x (f32)   STORE: out (bf16)   GELU: gg (bf16)   QKV: q (bf16)   LOGITS: logits (f32)
   void* out1;       // RESIDUAL: xb (bf16)                                     QKV: K cache
   void* out2;       //                                                         QKV: V cache
-  long long s0, s1; // QKV: head_stride (Tmax*64), row_stride (H*Tmax*64)
+  long long s0, s1; // QKV: head stride and row stride inside one cache slab (chunk-major self-attention cache)
+  long long slab;   // QKV: elements per slab (one 4 KB chunk of every (row, head));  t_shift = log2(keys per chunk)
+  int t_shift;
   int inner;        // QKV: H * 64
   int pad_;
 };
@@ -571,7 +573,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_tc_kernel(const __grid
                   step = (size_t)4 * ph.inner;
                 } else {
                   op = reinterpret_cast<bf16*>(seg == 1 ? ph.out1 : ph.out2) + (size_t)m_t0 * ph.s1 +
-                       (size_t)(c >> 6) * ph.s0 + (size_t)t * 64 + (c & 63);
+                       (size_t)(c >> 6) * ph.s0 + (size_t)(t >> ph.t_shift) * ph.slab +
+                       (size_t)(t & ((1 << ph.t_shift) - 1)) * 64 + (c & 63);
                   step = (size_t)4 * ph.s1;
                 }
               }

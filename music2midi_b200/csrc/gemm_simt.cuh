@@ -114,20 +114,23 @@ struct EpiGatedGelu {
   }
 };
 // Decode-step fused QKV: cols [0,I) -> q[m, :], [I,2I) -> K cache, [2I,3I) -> V cache at position t of the
-// head-major self-attention cache [b][h][t][64].
+// chunk-major self-attention cache [t / CH][b][h][t % CH][64] (CH = keys per 4 KB chunk: the bytes a decode step
+// reads are dense in the address space whatever t is).
 template <typename TC>
 struct EpiQKVCache {
   TC* q;
   TC* kc;
   TC* vc;
   int inner;           // I = H * 64
-  size_t head_stride;  // Tmax * 64
-  size_t row_stride;   // H * Tmax * 64
+  size_t head_stride;  // CH * 64
+  size_t row_stride;   // H * CH * 64
+  size_t slab;         // B * H * CH * 64
+  int t_shift;         // log2(CH)
   __device__ __forceinline__ void operator()(int m, int n, const float v[4], const DecState* st) const {
-    int seg = n / inner, c = n - seg * inner;
+    const int seg = (n >= inner) + (n >= 2 * inner), c = n - seg * inner, t = st->t;
     TC* dst = seg == 0 ? q + (size_t)m * inner + c
                        : (seg == 1 ? kc : vc) + (size_t)m * row_stride + (size_t)(c >> 6) * head_stride +
-                             (size_t)st->t * 64 + (c & 63);
+                             (size_t)(t >> t_shift) * slab + (size_t)(t & ((1 << t_shift) - 1)) * 64 + (c & 63);
     store4(dst, v);
   }
 };

@@ -188,8 +188,10 @@ __global__ void __launch_bounds__(256) seq_attn_kernel(const T* __restrict__ Q, 
 }
 
 // ------------------------------------------------------------------ KV-cached decode attention (a8)
-// HBM-bound streaming kernel.  One block (4 warps) per (row b, head h); caches are head-major
-// [b][h][j][64], so the K and the V of a (b, h) pair are two contiguous streams.  Thread 0 drives a
+// HBM-bound streaming kernel.  One block (4 warps) per (row b, head h).  The K and the V of a (b, h) pair are streams
+// of 4 KB chunks `chunk_stride` bytes apart: the cross-attention cache is head-major [b][h][j][64] (chunk_stride = 4 KB,
+// one contiguous stream), the self-attention cache is chunk-major [j / CH][b][h][j % CH][64] (chunk_stride = one slab),
+// so that the bytes a step reads are dense in the address space whatever t is.  Thread 0 drives a
 // STAGES-deep ring of 4 KB + 4 KB shared-memory buffers with 1-D bulk async copies (TMA engine,
 // cp.async.bulk + mbarrier complete_tx): bytes in flight do not cost registers, ~9 blocks/SM keep
 // ~200 KB per SM outstanding.  The 4 warps split every chunk (8 lanes per key, 16-byte conflict-free
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(256) seq_attn_kernel(const T* __restrict__ Q, 
 template <typename T, bool SELF, bool FAST_EXP, int STAGES = 3>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ q, const T* __restrict__ Kc,
                                                           const T* __restrict__ Vc, size_t row_stride,
-                                                          size_t head_stride, int nkeys_fixed,
+                                                          size_t head_stride, size_t chunk_stride, int nkeys_fixed,
                                                           const float* __restrict__ bias, int bias_ld,
                                                           T* __restrict__ out, int H,
                                                           const DecState* __restrict__ st,
@@ -247,8 +249,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const T* __restrict__ 
     const int nk = min(CH, nkeys - i * CH);
     const uint32_t bytes = (uint32_t)nk * 64u * (uint32_t)sizeof(T);
     mbar_expect_tx(&full_bar[s], 2 * bytes);
-    bulk_g2s_hint(ring[s][0], kg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s], pol);
-    bulk_g2s_hint(ring[s][1], vg + (size_t)i * CHUNK_BYTES, bytes, &full_bar[s], pol);
+    bulk_g2s_hint(ring[s][0], kg + (size_t)i * chunk_stride, bytes, &full_bar[s], pol);
+    bulk_g2s_hint(ring[s][1], vg + (size_t)i * chunk_stride, bytes, &full_bar[s], pol);
   };
   if (tid == 0)
     for (int i = 0; i < STAGES - 1 && i < nchunks; ++i) issue(i);
