@@ -61,7 +61,7 @@ enum ChainEpi : int {
   CH_RESIDUAL = 0,  // x[m, n] += acc; xb[m, n] = bf16(x); ss[m][slice] = sum_n x^2          (N per CTA = 64)
   CH_STORE = 1,     // out_bf16[m, n] = acc * rstd(m)                                          (cross-attention q)
   CH_GELU = 2,      // gg[m, n/2] = gelu_new(acc[2j] rstd) * (acc[2j+1] rstd)                  (Wi rows interleaved)
-  CH_QKV = 3,       // acc * rstd -> q | K cache | V cache at position st->t (head-major caches)
+  CH_QKV = 3,       // acc * rstd -> q | K cache | V cache at position st->t (chunk-major self-attention cache)
   CH_LOGITS = 4,    // logits_f32[m, n] = acc * rstd
 };
 
