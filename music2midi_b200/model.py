@@ -8,7 +8,7 @@ here, so this is a plain ``nn.Module`` that understands Lightning checkpoint fil
 
 Differences that do not change results: segments are independent, so instead of
 chunks of ``inference.batch_size`` (=128) the B200 path decodes ``inference.device_batch_size``
-segments at a time, and on several GPUs clips are sharded across ranks (music2midi_b200/distributed.py).
+segments at a time (2560 when the config does not set it), and on several GPUs clips are sharded across ranks (music2midi_b200/distributed.py).
 """
 from __future__ import annotations
 
@@ -24,6 +24,13 @@ from .evaluation import evaluate_batch
 from .input import ModelInputs
 from .transformer import T5Transformer
 from .utils import numpy_to_midi
+
+
+# Segments decoded as one device batch when the config has no ``inference.device_batch_size`` (the reference's
+# ``inference.batch_size`` = 128 bounds the memory of its own GPUs; results do not depend on the batch size, and the
+# decode step of this path is latency-bound below a few hundred rows): 2560 segments = 256 clips of 30 s, ~75 GB of KV
+# cache in bf16.
+DEFAULT_DEVICE_BATCH = 2560
 
 
 def load_audio(path: Union[str, Path], sr: int) -> np.ndarray:
@@ -136,7 +143,7 @@ class Music2MIDI(nn.Module):
             waveform = torch.nn.functional.pad(waveform, (0, split_size - tail))
         segments = waveform.reshape(-1, split_size)
         inf = self.config.get("inference", {}) or {}
-        chunk = int(inf.get("device_batch_size", inf.get("batch_size", 128)))
+        chunk = int(inf.get("device_batch_size", DEFAULT_DEVICE_BATCH))
         rows: List[torch.Tensor] = []
         for i in range(0, segments.shape[0], chunk):
             wav = segments[i:i + chunk].to(self.device)
@@ -192,7 +199,7 @@ class Music2MIDI(nn.Module):
             if cond_index is not None:
                 cond += np.asarray(torch.Tensor(cond_index).long().numpy(), dtype=np.int64)
             inf = self.config.get("inference", {}) or {}
-            chunk = int(inf.get("device_batch_size", inf.get("batch_size", 128)))
+            chunk = int(inf.get("device_batch_size", DEFAULT_DEVICE_BATCH))
             toks, _ = self.model.engine().transcribe_host(stage.numpy(), cond, 1024, device_batch=chunk)
             tok = torch.from_numpy(toks)
         else:
